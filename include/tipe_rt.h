@@ -1,0 +1,217 @@
+/* tipe_rt.h — C ABI of libtipe_rt.so, the B200 (sm_100a) replacement for the per-pixel
+ * path-tracing hot path of xelema/tipe-raytracer's main.c.
+ *
+ * What it replaces: the pthread fan-out `for t in NUM_THREADS: pthread_create(fill_canva)` +
+ * `pthread_join` of main.c:402-453, i.e. everything reached from fill_canva (main.c:245-284):
+ * get_ray (camera.h:42-54), tracer (main.c:118-242), closest_hit (main.c:52-92),
+ * ambient_occlusion (main.c:94-116), hit_sphere (sphere.h:13-47), hit_triangle (mesh.h:70-94),
+ * tri_uvmapping (texture.h:44-90), the refraction stack (pile.h), write_color_canva
+ * (rtutility.h:56-71).  Everything else in main.c (OBJ/MTL/PPM loading, init_camera, the
+ * OIDN post-pass, the PPM writer) stays host C and feeds / consumes this interface.
+ *
+ * Plain C, plain pointers and sizes.  The scene structs below are layout-identical to the
+ * reference's (sizes and offsets asserted at the bottom), so a caller inside the reference
+ * tree passes its own `sphere*`, `triangle*`, `material*`, `camera` by cast — see
+ * INTEGRATION.md for the exact stub.
+ *
+ * Conventions (all from the reference):
+ *   - pixel_index = j*W + i with j = 0 the BOTTOM image row (main.c:261, file written j=H-1..0, main.c:460);
+ *   - canva holds integer values 0..255 stored in doubles (write_color_canva), albedo_tab /
+ *     normal_tab hold per-pixel means (main.c:275-279);
+ *   - object id: sphere k -> k, triangle k -> nbSpheres + k, miss -> -1;
+ *   - ThreadData truncates AO_intensity, focus_distance, ouverture_x/y to int (main.c:42-43):
+ *     this ABI takes doubles, a caller that wants main.c's behaviour passes (double)(int)x.
+ *
+ * Errors: every call returns TRT_OK (0) or a negative code; the text is in trt_last_error().
+ * The library never calls exit().  There is no CPU fallback: without a CUDA device trt_init fails.
+ */
+#ifndef TIPE_RT_H
+#define TIPE_RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#  define TRT_API __attribute__((visibility("default")))
+#else
+#  define TRT_API
+#endif
+
+/* ---- scene types: byte-compatible with the reference ---------------------------------- */
+typedef struct trt_vec3 { double e[3]; } trt_vec3;                 /* vec3.h:7-9 (vec3/point3/color) */
+
+typedef struct trt_material {                                       /* hitinfo.h:6-13 */
+    trt_vec3 diffuseColor;
+    trt_vec3 emissionColor;
+    double   emissionStrength;
+    double   reflectionStrength;
+    double   alpha;
+    double   materialIndex;
+} trt_material;
+
+typedef struct trt_sphere {                                         /* sphere.h:7-11 */
+    trt_vec3     center;
+    double       radius;
+    trt_material mat;
+} trt_sphere;
+
+typedef struct trt_uv { double u, v; } trt_uv;                      /* mesh.h:9-12 */
+
+typedef struct trt_triangle {                                       /* mesh.h:14-22 */
+    trt_vec3     A, B, C;
+    trt_material mat;      /* ignored: the reference always overwrites it from the texture (main.c:86-88) */
+    trt_uv       uvA, uvB, uvC;
+} trt_triangle;
+
+typedef struct trt_camera {                                         /* camera.h:10-15 */
+    trt_vec3 origin, horizontal, vertical, coin_bas_gauche;
+} trt_camera;
+
+/* ---- per-material overrides (texture.h:71-87 hard-codes three of them) ------------------ */
+enum {
+    TRT_OV_EMISSION_COLOR    = 1u << 0,
+    TRT_OV_EMISSION_STRENGTH = 1u << 1,
+    TRT_OV_REFLECTION        = 1u << 2,
+    TRT_OV_ALPHA             = 1u << 3,
+    TRT_OV_MATERIAL_INDEX    = 1u << 4
+};
+typedef struct trt_mat_override {
+    int      material_ordinal;       /* numero_mat = quelMatPourTri[tri] (texture.h:64) */
+    unsigned mask;                   /* which of the fields below replace the texel's */
+    double   emissionColor[3];
+    double   emissionStrength;
+    double   reflectionStrength;
+    double   alpha;
+    double   materialIndex;
+} trt_mat_override;
+
+/* Fills `out` (room for >= 3) with the reference's built-in table (texture.h:71-87):
+ * ordinal 1 -> emission WHITE x1.85, alpha 1; ordinal 4 -> alpha .6, index 1.33, refl .93;
+ * ordinal 3 -> alpha .1, index 1.50, refl .3.  Returns the count (3). */
+TRT_API int trt_default_overrides(trt_mat_override* out, int capacity);
+
+/* ---- render parameters: the knobs of main.c:293-317 as carried by ThreadData ----------- */
+enum {
+    TRT_FLAG_COUNT_RAYS  = 1 << 0,   /* fill trt_stats.rays (one 64-bit atomic per warp per item) */
+    TRT_FLAG_BRUTE_FORCE = 1 << 1,   /* triangles by linear scan like main.c:81-90 instead of the BVH */
+    TRT_FLAG_COUNT_TESTS = 1 << 2    /* also count box / triangle / sphere tests (slower; for the roofline) */
+};
+typedef struct trt_params {
+    int        largeur_image, hauteur_image;     /* W, H */
+    int        nbRayonParPixel;                  /* samples rendered by THIS call */
+    int        nbRebondMax;                      /* loop trip count of main.c:132 */
+    int        useAO;
+    double     AO_intensity;
+    double     focus_distance, ouverture_x, ouverture_y;
+    trt_camera cam;                              /* as produced by init_camera (camera.h:21-40) */
+    uint64_t   seed;                             /* Philox key; same seed => bit-identical image */
+    int        sample_offset;                    /* global index of this call's first sample (spp split) */
+    int        sample_total;                     /* divisor used by the resolve; 0 => nbRayonParPixel */
+    int        flags;
+    int        reserved;
+} trt_params;
+
+typedef struct trt_stats {
+    uint64_t paths;            /* W*H*nbRayonParPixel traced by this call (all devices of the ctx) */
+    uint64_t rays;             /* closest_hit evaluations: primary + bounce + AO (TRT_FLAG_COUNT_RAYS) */
+    uint64_t box_tests, tri_tests, sphere_tests;   /* TRT_FLAG_COUNT_TESTS */
+    double   ms_trace;         /* path-tracing kernel(s), CUDA events, max over the ctx's devices */
+    double   ms_reduce_resolve;/* peer reduce + tonemap kernel */
+    double   ms_d2h;           /* device -> caller buffers */
+    double   ms_total;         /* whole call, host clock */
+    int      kernel_launches;  /* kernels of this library launched by the call */
+    int      reserved;
+} trt_stats;
+
+typedef struct trt_ctx trt_ctx;
+
+/* ---- life cycle ------------------------------------------------------------------------ */
+/* device_ids == NULL => devices 0..n_devices-1.  n_devices > 1 renders disjoint sample ranges
+ * on each device and sums them on device_ids[0] through peer (NVLink) loads. */
+TRT_API int         trt_init(const int* device_ids, int n_devices, trt_ctx** out);
+TRT_API void        trt_destroy(trt_ctx* ctx);
+TRT_API const char* trt_last_error(const trt_ctx* ctx);     /* ctx may be NULL: last trt_init error */
+TRT_API int         trt_version(void);
+
+/* ---- scene ----------------------------------------------------------------------------- */
+/* Copies and converts the caller's arrays (read-only, not retained) to the device layout and
+ * builds the BVH on the GPU.  mat_list has nbMaterials*tex_w*tex_h entries (texture.h:64-68).
+ * overrides == NULL && n_overrides < 0 => the reference's built-in table. */
+TRT_API int trt_scene_set(trt_ctx* ctx,
+                          const trt_sphere* sphere_list, int nbSpheres,
+                          const trt_triangle* triangle_list, int nbTriangles,
+                          const trt_material* mat_list, int tex_width, int tex_height, int nbMaterials,
+                          const int* quelMatPourTri,
+                          const trt_mat_override* overrides, int n_overrides);
+
+/* ---- the drop-in call: replaces main.c:402-453 ------------------------------------------- */
+/* canva / albedo_tab / normal_tab: caller-owned host arrays of W*H colors; stats may be NULL. */
+TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
+                       trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats);
+
+/* Primary-hit buffers through pixel centres (u = i/(W-1), v = j/(H-1), no jitter, no aperture):
+ * FP64, linear scan in the reference's order, so ids match the CPU path exactly. Any output may be NULL. */
+TRT_API int trt_primary(trt_ctx* ctx, const trt_params* params,
+                        double* t, int* id, trt_vec3* normal, trt_vec3* albedo);
+
+/* ---- device-resident pieces (what trt_render is made of; used by the multi-process path
+ *      where the sample sums cross GPUs with an NCCL reduce, and by bench.py) -------------- */
+#define TRT_ACCUM_CHANNELS 9      /* radiance rgb, albedo rgb, normal xyz */
+#define TRT_ACCUM_FRAC_BITS 28    /* sums are int64 fixed point, value * 2^28 per sample */
+
+/* Adds this call's samples into d_accum (device pointer on the ctx's first device, int64,
+ * planar [9][W*H], must be zeroed by the caller before the first call of an image). */
+TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_accum, trt_stats* stats);
+
+/* Tonemaps device sums into host (or, _device, device) color arrays like main.c:275-279. */
+TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                        trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab);
+TRT_API int trt_resolve_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                               double* d_canva, double* d_albedo, double* d_normal);
+
+/* Stream the ctx's first device works on (a cudaStream_t), for callers that interleave their own work. */
+TRT_API void* trt_stream(trt_ctx* ctx);
+TRT_API int   trt_synchronize(trt_ctx* ctx);
+
+/* BVH facts of the current scene: nodes, leaves, max depth, root surface-area cost. */
+typedef struct trt_bvh_info { int n_nodes, n_leaves, max_depth, n_twins; double sah_cost; double ms_build; } trt_bvh_info;
+TRT_API int trt_bvh_info_get(trt_ctx* ctx, trt_bvh_info* out);
+
+/* ---- device known-answer entry points (FP32 leaf functions of the path-tracing kernel,
+ *      run on the GPU over n independent inputs; outputs are float) -------------------------- */
+TRT_API int trt_kat_hit_sphere(trt_ctx* ctx, int n, const float* center_radius /*[n][4]*/,
+                               const float* ray_o_d /*[n][6]*/, int* hit, float* dst, float* point, float* normal);
+TRT_API int trt_kat_hit_triangle(trt_ctx* ctx, int n, const float* abc /*[n][9]*/,
+                                 const float* ray_o_d /*[n][6]*/, int* hit, float* dst_u_v /*[n][3]*/);
+TRT_API int trt_kat_refract(trt_ctx* ctx, int n, const float* v_n_n1_n2 /*[n][8]*/, float* out /*[n][3]*/);
+TRT_API int trt_kat_philox(trt_ctx* ctx, int n, const uint32_t* ctr_key /*[n][6]*/, uint32_t* out /*[n][4]*/);
+TRT_API int trt_kat_tonemap(trt_ctx* ctx, int n, const int64_t* sums /*[n]*/, int spp, double* out /*[n]*/);
+
+/* ---- layout contract -------------------------------------------------------------------- */
+#if defined(__cplusplus)
+#  define TRT_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#  define TRT_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
+TRT_STATIC_ASSERT(sizeof(trt_vec3) == 24, "vec3 is 3 doubles");
+TRT_STATIC_ASSERT(sizeof(trt_material) == 80, "material layout (hitinfo.h:6-13)");
+TRT_STATIC_ASSERT(offsetof(trt_material, alpha) == 64, "material.alpha offset");
+TRT_STATIC_ASSERT(sizeof(trt_sphere) == 112 && offsetof(trt_sphere, mat) == 32, "sphere layout (sphere.h:7-11)");
+TRT_STATIC_ASSERT(sizeof(trt_triangle) == 200 && offsetof(trt_triangle, uvA) == 152, "triangle layout (mesh.h:14-22)");
+TRT_STATIC_ASSERT(sizeof(trt_camera) == 96, "camera layout (camera.h:10-15)");
+
+#define TRT_OK                 0
+#define TRT_ERR_INVALID       -1
+#define TRT_ERR_NO_DEVICE     -2
+#define TRT_ERR_CUDA          -3
+#define TRT_ERR_NO_SCENE      -4
+#define TRT_ERR_OOM           -5
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIPE_RT_H */

@@ -1,0 +1,264 @@
+/* TEST INFRASTRUCTURE — builds oracle/_ref/libtipe_ref.so. Never linked into the product.
+ *
+ * Compiles the UNMODIFIED reference translation unit (/root/reference/main.c with its
+ * headers, found through -I) as a library, and exports a small plain-C surface over the
+ * reference's own functions so that tests and bench.py's cpu_baseline / --impl reference
+ * legs can call the real thing:
+ *
+ *   - ref_render      : the pthread fan-out of main.c:402-453 around the reference's
+ *                       fill_canva (main.c:245-284), any thread count, optional srand.
+ *   - ref_primary     : pixel-centre get_ray (camera.h:42-54) + the reference's hit_sphere /
+ *                       hit_triangle / tri_uvmapping, looped like main.c:59-90 with index capture.
+ *   - ref_kat_*       : direct calls into the leaf functions for known-answer tests.
+ *   - ref_load_*      : the reference OBJ/MTL/PPM loaders (mesh.h:96-218, texture.h:175-354).
+ *
+ * No reference source is copied here: main.c is pulled in by #include from where it lies.
+ * Ray counting uses the single `closestHit.dst=INFINITY;` statement of closest_hit
+ * (main.c:56) as the hook: INFINITY is re-defined below to bump a counter, so the
+ * reference text itself stays untouched.
+ */
+#define _GNU_SOURCE
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+#include <fcntl.h>
+#include <pthread.h>
+#include <sys/time.h>
+
+static int g_count_on = 0;
+static unsigned long long g_ray_count = 0;
+static inline double trt_ref_inf_hook(void)
+{
+    if (g_count_on) __atomic_fetch_add(&g_ray_count, 1ULL, __ATOMIC_RELAXED);
+    return __builtin_inf();
+}
+#undef INFINITY
+#define INFINITY (trt_ref_inf_hook())
+
+#define main reference_main
+#include "main.c"
+#undef main
+
+#undef INFINITY
+#define INFINITY (__builtin_inff())
+
+#define REF_API __attribute__((visibility("default")))
+
+/* ---- layout probe ------------------------------------------------------------------ */
+REF_API void ref_sizes(int* out)
+{
+    out[0] = (int)sizeof(vec3);     out[1] = (int)sizeof(ray);      out[2] = (int)sizeof(material);
+    out[3] = (int)sizeof(HitInfo);  out[4] = (int)sizeof(sphere);   out[5] = (int)sizeof(UV);
+    out[6] = (int)sizeof(triangle); out[7] = (int)sizeof(camera);   out[8] = (int)sizeof(col_alb_norm);
+    out[9] = (int)__builtin_offsetof(triangle, uvA);
+    out[10] = (int)__builtin_offsetof(sphere, mat);
+    out[11] = (int)__builtin_offsetof(material, alpha);
+}
+
+REF_API void ref_srand(unsigned seed) { srand(seed); }
+REF_API void ref_count_rays(int on) { g_count_on = on; }
+REF_API unsigned long long ref_ray_count(void) { return g_ray_count; }
+REF_API void ref_ray_count_reset(void) { g_ray_count = 0; }
+
+REF_API void ref_init_camera(const double* origin, const double* target, const double* up,
+                             double vfov, double ratio, camera* out)
+{
+    point3 o = {{origin[0], origin[1], origin[2]}};
+    point3 t = {{target[0], target[1], target[2]}};
+    vec3 u = {{up[0], up[1], up[2]}};
+    *out = init_camera(o, t, u, vfov, ratio);
+}
+
+/* ---- full render: same fan-out as main.c:402-453 -------------------------------------- */
+static int silence_stderr(void)
+{
+    fflush(stderr);
+    int saved = dup(2);
+    int nul = open("/dev/null", O_WRONLY);
+    if (nul >= 0) { dup2(nul, 2); close(nul); }
+    return saved;
+}
+static void restore_stderr(int saved)
+{
+    fflush(stderr);
+    if (saved >= 0) { dup2(saved, 2); close(saved); }
+}
+
+REF_API double ref_render(const sphere* spheres, int nbSpheres, const triangle* tris, int nbTriangles,
+                          const material* mat_list, int tex_w, int tex_h, const int* quelMatPourTri,
+                          const camera* cam, int W, int H, int spp, int nbRebondMax,
+                          int useAO, int AO_intensity, int focus_distance, int ouverture_x, int ouverture_y,
+                          int num_threads, int quiet,
+                          color* canva, color* albedo_tab, color* normal_tab)
+{
+    if (num_threads < 1) num_threads = 1;
+    if (num_threads > H) num_threads = H;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * num_threads);
+    struct ThreadData* td = (struct ThreadData*)calloc(num_threads, sizeof(struct ThreadData));
+    int saved = quiet ? silence_stderr() : -1;
+    rendered_pixels = 0;
+
+    struct timeval t0, t1;
+    gettimeofday(&t0, NULL);
+    int rows = H / num_threads, rem = H % num_threads, start_row = H - 1;
+    for (int k = 0; k < num_threads; k++) {
+        int end_row = start_row - rows + 1;
+        if (k == num_threads - 1) end_row -= rem;
+        td[k].start_row = start_row;           td[k].end_row = end_row;
+        td[k].canva = canva;                   td[k].albedo_tab = albedo_tab;   td[k].normal_tab = normal_tab;
+        td[k].tex_list = NULL;                 td[k].mat_list = (material*)mat_list;
+        td[k].sky_mat_list = NULL;             td[k].cam = *cam;
+        td[k].largeur_image = W;               td[k].hauteur_image = H;
+        td[k].tex_width = tex_w;               td[k].tex_height = tex_h;
+        td[k].sky_width = 0;                   td[k].sky_height = 0;
+        td[k].quelMatPourTri = (int*)quelMatPourTri;
+        td[k].nbRayonParPixel = spp;           td[k].nbRebondMax = nbRebondMax;
+        td[k].total_pixels = W * H;
+        td[k].sphere_list = (sphere*)spheres;  td[k].nbSpheres = nbSpheres;
+        td[k].triangle_list = (triangle*)tris; td[k].nbTriangles = nbTriangles;
+        td[k].ouverture_x = ouverture_x;       td[k].ouverture_y = ouverture_y;
+        td[k].focus_distance = focus_distance; td[k].AO_intensity = AO_intensity;
+        td[k].useAO = useAO != 0;
+        pthread_create(&th[k], NULL, fill_canva, &td[k]);
+        start_row = end_row - 1;
+    }
+    for (int k = 0; k < num_threads; k++) pthread_join(th[k], NULL);
+    gettimeofday(&t1, NULL);
+
+    restore_stderr(saved);
+    free(th); free(td);
+    return (double)(t1.tv_sec - t0.tv_sec) + 1e-6 * (double)(t1.tv_usec - t0.tv_usec);
+}
+
+/* ---- primary-hit buffers -------------------------------------------------------------- */
+REF_API void ref_primary(const sphere* spheres, int nbSpheres, const triangle* tris, int nbTriangles,
+                         const material* mat_list, int tex_w, int tex_h, const int* quelMatPourTri,
+                         const camera* cam, int W, int H, double focus_distance,
+                         double* t_out, int* id_out, color* normal_out, color* albedo_out)
+{
+    for (int j = 0; j < H; j++) for (int i = 0; i < W; i++) {
+        double u = (double)i / (W - 1), v = (double)j / (H - 1);
+        ray r = get_ray(u, v, *cam, focus_distance, 0.0, 0.0);
+        int id = -1; double best = __builtin_inf();
+        color nrm = {{0, 0, 0}}, alb = {{0, 0, 0}};
+        for (int s = 0; s < nbSpheres; s++) {
+            HitInfo h = hit_sphere(spheres[s].center, spheres[s].radius, r);
+            if (h.didHit && h.dst < best) { best = h.dst; id = s; nrm = h.normal; alb = spheres[s].mat.diffuseColor; }
+        }
+        for (int k = 0; k < nbTriangles; k++) {
+            HitInfo h = hit_triangle(tris[k], r);
+            if (h.didHit && h.dst < best) {
+                material m = tri_uvmapping(tris[k], h, (material*)mat_list, tex_w, tex_h, k, (int*)quelMatPourTri);
+                best = h.dst; id = nbSpheres + k; nrm = h.normal; alb = m.diffuseColor;
+            }
+        }
+        int p = j * W + i;
+        t_out[p] = best; id_out[p] = id; normal_out[p] = nrm; albedo_out[p] = alb;
+    }
+}
+
+/* ---- leaf known-answer entry points ---------------------------------------------------- */
+REF_API void ref_kat_get_ray(double u, double v, const camera* cam, double focus, double dx, double dy, ray* out)
+{ *out = get_ray(u, v, *cam, focus, dx, dy); }
+
+REF_API int ref_kat_hit_sphere(const double* center, double radius, const ray* r, double* dst, double* point, double* normal)
+{
+    point3 c = {{center[0], center[1], center[2]}};
+    HitInfo h = hit_sphere(c, radius, *r);
+    if (h.didHit) { *dst = h.dst; memcpy(point, h.hitPoint.e, 24); memcpy(normal, h.normal.e, 24); }
+    return h.didHit ? 1 : 0;
+}
+
+REF_API int ref_kat_hit_triangle(const triangle* tri, const ray* r, double* dst, double* point, double* normal)
+{
+    HitInfo h = hit_triangle(*tri, *r);
+    *dst = h.dst; memcpy(point, h.hitPoint.e, 24); memcpy(normal, h.normal.e, 24);
+    return h.didHit ? 1 : 0;
+}
+
+REF_API void ref_kat_tri_uvmapping(const triangle* tri, const double* point, const double* normal,
+                                   const material* mat_list, int tw, int th, int tri_index, const int* quelMat, material* out)
+{
+    HitInfo h; memset(&h, 0, sizeof h); h.didHit = true;
+    memcpy(h.hitPoint.e, point, 24); memcpy(h.normal.e, normal, 24);
+    *out = tri_uvmapping(*tri, h, (material*)mat_list, tw, th, tri_index, (int*)quelMat);
+}
+
+REF_API void ref_kat_reflect(const double* v, const double* n, double* out)
+{
+    vec3 a = {{v[0], v[1], v[2]}}, b = {{n[0], n[1], n[2]}};
+    vec3 r = reflected_vec(a, b); memcpy(out, r.e, 24);
+}
+
+REF_API void ref_kat_refract(const double* v, const double* n, double n1, double n2, double* out)
+{
+    vec3 a = {{v[0], v[1], v[2]}}, b = {{n[0], n[1], n[2]}};
+    vec3 r = refracted_vec(a, b, n1, n2); memcpy(out, r.e, 24);
+}
+
+REF_API void ref_kat_tonemap(const double* sum, int spp, double* out)
+{
+    color c = {{sum[0], sum[1], sum[2]}};
+    color r = write_color_canva(c, spp); memcpy(out, r.e, 24);
+}
+
+REF_API void ref_kat_hsl_roundtrip(const double* rgb, double* out)
+{
+    color c = {{rgb[0], rgb[1], rgb[2]}};
+    color r = hsl_to_rgb(rgb_to_hsl(c)); memcpy(out, r.e, 24);
+}
+
+REF_API void ref_kat_random_dir(double* out) { vec3 d = random_dir_no_norm(); memcpy(out, d.e, 24); }
+REF_API double ref_kat_random_double(double lo, double hi) { return randomDouble(lo, hi); }
+
+/* ops: sequence of (kind, value): kind 0 = index_suivant_pile(value) then info_pile_actuelle,
+ * kind 1 = index_suivant_pile(value), info_pile_actuelle, then depiler (the "exit" branch of
+ * main.c:175-181). out[2*k..] receives the (n1,n2) pair tracer would use (main.c:171-180). */
+REF_API void ref_kat_pile(const int* kind, const double* value, int n, double* out)
+{
+    pile* p = init_pile();
+    empiler(p, 1.0, 1.0);
+    for (int k = 0; k < n; k++) {
+        index_suivant_pile(p, value[k]);
+        IndRef top = info_pile_actuelle(p);
+        double n1 = top.n[0], n2 = top.n[1];
+        if (kind[k] == 1) { IndRef popped = depiler(p); n1 = popped.n[1]; n2 = popped.n[0]; }
+        out[2 * k] = n1; out[2 * k + 1] = n2;
+    }
+    while (p->premier != NULL) depiler(p);
+    free(p);
+}
+
+/* One tracer() call on the current rand() stream (main.c:118-242). */
+REF_API void ref_kat_tracer(const ray* r, int nbRebondMax, const sphere* spheres, int nbSpheres,
+                            const triangle* tris, int nbTriangles, double AO_intensity, int useAO,
+                            const material* mat_list, int tw, int th, const int* quelMat, double* out9)
+{
+    col_alb_norm c = tracer(*r, nbRebondMax, (sphere*)spheres, nbSpheres, (triangle*)tris, nbTriangles,
+                            AO_intensity, useAO != 0, (material*)mat_list, tw, th, (int*)quelMat, NULL, 0, 0);
+    memcpy(out9, &c, 72);
+}
+
+/* ---- loaders --------------------------------------------------------------------------- */
+/* list_of_mesh (mesh.h:96-218) prints to stdout; callers that care redirect it. */
+REF_API triangle* ref_load_mesh(const char* obj, const char* mtl, int* nbTriangles, int* nbMaterials,
+                                char*** mat_paths, int** quelMatPourTri)
+{
+    int* first_tri_of_mat = NULL;
+    fflush(stdout);
+    int saved = dup(1); int nul = open("/dev/null", O_WRONLY);
+    if (nul >= 0) { dup2(nul, 1); close(nul); }
+    triangle* t = list_of_mesh(obj, mtl, nbTriangles, nbMaterials, mat_paths, &first_tri_of_mat, quelMatPourTri);
+    fflush(stdout);
+    if (saved >= 0) { dup2(saved, 1); close(saved); }
+    free(first_tri_of_mat);
+    return t;
+}
+
+REF_API material* ref_load_textures(char** mat_paths, int nbMaterials, int* tw, int* th)
+{ return create_mat_list_mtl(mat_paths, tw, th, nbMaterials); }
+
+REF_API const char* ref_mat_path(char** mat_paths, int k) { return mat_paths[k]; }
+REF_API void ref_free(void* p) { free(p); }
