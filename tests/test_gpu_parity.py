@@ -1,0 +1,244 @@
+"""GPU parity: libtipe_rt.so (through its C ABI) against the CPU oracle and the golden vectors.
+
+Three families, as BASELINE.json's north_star asks:
+  1. primary-hit buffers: ids bit-exact, floats within 1e-4 relative of the FP64 reference
+     (the FP64 pass is in fact expected to be bit-identical; both are asserted);
+  2. radiance: sample-exact comparison with the oracle driven by the SAME Philox stream (tight), and a
+     statistical comparison with the reference's own rand()-stream render (RMSE vs the CPU noise floor);
+  3. reproducibility: byte-identical images across runs, across sample splits, across schedules.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle.oracle_py import RNG_LIBC, RNG_PHILOX
+from tipe_raytracer_b200 import FLAG_BRUTE_FORCE, FLAG_COUNT_TESTS, TrtError
+from tipe_raytracer_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+libc = ctypes.CDLL(None)
+
+
+def _close(a, b, rtol):
+    return np.all(np.abs(a - b) <= rtol * np.maximum(np.abs(b), 1e-300))
+
+
+# ---- 0. leaf functions -------------------------------------------------------------------------------
+def test_philox_matches_oracle(rt, oracle):
+    rng = np.random.default_rng(1)
+    ck = rng.integers(0, 2**32, (512, 6), dtype=np.uint64).astype(np.uint32)
+    ck[0] = 0; ck[1] = 0xffffffff
+    ck[2] = [0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344, 0xa4093822, 0x299f31d0]
+    got = rt.kat_philox(ck)
+    assert got[2].tolist() == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    for k in range(0, 512, 7):
+        assert np.array_equal(got[k], oracle.philox(ck[k, :4], ck[k, 4:]))
+
+
+def test_hit_sphere_fp32_vs_reference(rt, golden):
+    g = golden["leaves"]
+    cr = np.concatenate([g["sph_center"], g["sph_radius"][:, None]], axis=1)
+    rays = np.concatenate([g["sph_o"], g["sph_d"]], axis=1)
+    hit, dst, pt, nr = rt.kat_hit_sphere(cr, rays)
+    want = g["sph_hit"].astype(bool)
+    flips = np.nonzero(hit != want)[0]          # FP32 may flip a grazing case
+    assert len(flips) <= 2, flips
+    ok = hit & want
+    assert ok.sum() > 100
+    rel = np.abs(dst[ok] - g["sph_dst"][ok]) / np.abs(g["sph_dst"][ok])
+    assert rel.max() < 2e-4, rel.max()          # includes r=500 / r=1e5 spheres (cancellation-prone)
+    assert np.median(rel) < 2e-6
+    assert np.abs(nr[ok] - g["sph_normal"][ok]).max() < 2e-3
+
+
+def test_hit_triangle_fp32_vs_reference(rt, golden):
+    g = golden["leaves"]
+    abc = np.concatenate([g["tri_A"], g["tri_B"], g["tri_C"]], axis=1)
+    rays = np.concatenate([g["tri_o"], g["tri_d"]], axis=1)
+    hit, duv = rt.kat_hit_triangle(abc, rays)
+    want = g["tri_hit"].astype(bool)
+    assert (hit != want).sum() <= 2
+    ok = hit & want
+    assert ok.sum() > 40
+    rel = np.abs(duv[ok, 0] - g["tri_dst"][ok]) / np.abs(g["tri_dst"][ok])
+    assert rel.max() < 1e-4
+
+
+def test_refract_fp32_vs_reference(rt, golden):
+    g = golden["leaves"]
+    inp = np.concatenate([g["rf_v"], g["rf_n"], g["rf_n1"][:, None], g["rf_n2"][:, None]], axis=1)
+    got = rt.kat_refract(inp)
+    assert np.abs(got - g["rf_refract"]).max() < 5e-6
+
+
+def test_tonemap_matches_reference_on_fixed_point_sums(rt, golden):
+    g = golden["leaves"]
+    spp = int(g["tm_spp"])
+    sums = g["tm_sum"].reshape(-1)
+    fixed = np.rint(sums * 2.0**28).astype(np.int64)
+    got = rt.kat_tonemap(fixed, spp)
+    want = g["tm_out"].reshape(-1)
+    # quantising the sum to 2^-28 can move a value across a truncation boundary: +-1 at most, rarely
+    assert np.abs(got - want).max() <= 1
+    assert (got != want).mean() < 0.02
+
+
+# ---- 1. primary-hit buffers ---------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4"])
+def test_primary_matches_golden(rt, golden, cfg):
+    g = golden["primary"]
+    sc = S.CONFIGS[cfg]()
+    rp = S.params_for(sc, width=int(g[f"{cfg}_width"]), spp=1)
+    rt.scene_set(sc)
+    r = rt.primary(rp)
+    assert np.array_equal(r["id"], g[f"{cfg}_id"])                                   # bit-exact ids
+    assert _close(r["t"], g[f"{cfg}_t"], 1e-4) and _close(r["normal"], g[f"{cfg}_normal"], 1e-4)
+    assert np.abs(r["albedo"] - g[f"{cfg}_albedo"]).max() < 1e-6
+    # stronger than required: the FP64 pass reproduces the CPU arithmetic exactly
+    assert np.array_equal(r["t"], g[f"{cfg}_t"]) and np.array_equal(r["normal"], g[f"{cfg}_normal"])
+
+
+def test_primary_full_resolution_c1(rt, oracle, golden):
+    g = golden["primary"]
+    sc = S.cornell_spheres()
+    rp = S.params_for(sc, spp=1)
+    assert (rp.width, rp.height) == (1000, 750)
+    rt.scene_set(sc)
+    r = rt.primary(rp)
+    want = oracle.primary(sc, rp)
+    assert np.array_equal(r["id"], want["id"]) and np.array_equal(r["t"], want["t"])
+    assert np.array_equal(np.bincount(r["id"] + 1, minlength=12), g["C1_full_id_histogram"])
+    idx = g["C1_full_px"][:, 1] * 1000 + g["C1_full_px"][:, 0]
+    assert r["id"][idx].tolist() == [9, 0, 2, 1, 0, 5]                               # SURVEY §4 vectors
+
+
+# ---- 2a. radiance, same random numbers -----------------------------------------------------------------
+def _compare_same_stream(rt, oracle, sc, rp, min_within1, max_mean_abs):
+    rt.scene_set(sc)
+    g = rt.render(rp)
+    o = oracle.render(sc, rp, rng=RNG_PHILOX)
+    d = np.abs(g["canva"] - o["canva"])
+    within1 = (d.max(axis=1) <= 1).mean()
+    assert within1 >= min_within1, (within1, d.mean())
+    assert d.mean() <= max_mean_abs, d.mean()
+    rays_gpu, rays_cpu = g["stats"]["rays"], o["stats"]["rays"]
+    assert abs(rays_gpu / rays_cpu - 1) < 5e-3, (rays_gpu, rays_cpu)
+    assert np.abs(g["albedo"] - o["albedo"]).mean() < 2e-3 and np.abs(g["normal"] - o["normal"]).mean() < 2e-3
+    return g, o
+
+
+def test_render_c1_same_stream(rt, oracle):
+    sc = S.cornell_spheres()
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=160, spp=16), 0.97, 0.25)
+
+
+def test_render_c1_no_ao_with_aperture(rt, oracle):
+    sc = S.cornell_spheres()
+    sc.use_ao = False
+    sc.aperture = (1.0, 2.0)            # >= 1 so main.c's int truncation keeps them
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=120, spp=12), 0.97, 0.25)
+
+
+def test_render_c3_refraction_stack_same_stream(rt, oracle):
+    sc = S.nested_dielectrics()
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=120, spp=12), 0.95, 0.4)
+
+
+def test_render_c2_mesh_same_stream(rt, oracle):
+    sc = S.nature_mesh()
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    assert rt.bvh_info()["n_twins"] > 1000          # double-faced mesh: twins found
+
+
+def test_render_c4_tree_same_stream(rt, oracle):
+    sc = S.tree_mesh()
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+
+
+def test_bvh_equals_linear_scan(rt):
+    """The BVH must not change results: same kernel with the triangle loop of main.c:81-90."""
+    sc = S.nature_mesh()
+    rt.scene_set(sc)
+    rp = S.params_for(sc, width=128, spp=8)
+    a = rt.render(rp)
+    rp.flags = FLAG_BRUTE_FORCE
+    b = rt.render(rp)
+    assert np.array_equal(a["canva"], b["canva"]) and np.array_equal(a["albedo"], b["albedo"])
+    assert a["stats"]["rays"] == b["stats"]["rays"]
+    rp.flags = FLAG_COUNT_TESTS
+    c = rt.render(rp)
+    assert np.array_equal(a["canva"], c["canva"])
+    per_ray = c["stats"]["tri_tests"] / c["stats"]["rays"]
+    assert 0 < per_ray < 60, per_ray                 # vs 5 812 for the linear scan
+
+
+# ---- 2b. radiance, statistical, against the reference's own rand() stream --------------------------------
+def test_render_c1_statistical_vs_reference(rt, oracle):
+    sc = S.cornell_spheres()
+    rp = S.params_for(sc, width=100, spp=48)
+    libc.srand(1)
+    cpu1 = oracle.render(sc, rp, rng=RNG_LIBC, threads=1)["canva"]      # == oracle/_ref bit for bit (test_oracle_pin)
+    libc.srand(2)
+    cpu2 = oracle.render(sc, rp, rng=RNG_LIBC, threads=1)["canva"]
+    rt.scene_set(sc)
+    gpu = rt.render(rp)["canva"]
+    floor = np.sqrt(((cpu1 - cpu2) ** 2).mean())
+    rmse = np.sqrt(((gpu - cpu1) ** 2).mean())
+    assert rmse <= 1.25 * floor, (rmse, floor)
+    assert np.all(np.abs(gpu.mean(0) - cpu1.mean(0)) / cpu1.mean(0) <= 0.02)
+
+
+# ---- 3. reproducibility ---------------------------------------------------------------------------------
+def test_bit_identical_across_runs_and_sample_splits(rt):
+    import torch
+    sc = S.cornell_spheres()
+    rt.scene_set(sc)
+    rp = S.params_for(sc, width=200, spp=40)
+    a = rt.render(rp)
+    b = rt.render(rp)
+    for k in ("canva", "albedo", "normal"):
+        assert a[k].tobytes() == b[k].tobytes()
+    # the spp split used across GPUs: 3 uneven ranges accumulated separately, summed as integers
+    n = rp.width * rp.height
+    total = torch.zeros(9 * n, dtype=torch.int64, device="cuda")
+    for off, cnt in ((0, 7), (7, 20), (27, 13)):
+        part = torch.zeros(9 * n, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        rt.accumulate(S.params_for(sc, width=200, spp=cnt, sample_offset=off, sample_total=40), part.data_ptr())
+        total += part
+    torch.cuda.synchronize()
+    c = rt.resolve(S.params_for(sc, width=200, spp=40), total.data_ptr())
+    for k in ("canva", "albedo", "normal"):
+        assert a[k].tobytes() == c[k].tobytes()
+    # a different seed is a different image
+    d = rt.render(S.params_for(sc, width=200, spp=40, seed=7))
+    assert d["canva"].tobytes() != a["canva"].tobytes()
+
+
+# ---- edge cases -------------------------------------------------------------------------------------------
+def test_edge_cases_and_errors(oracle):
+    from tipe_raytracer_b200 import Renderer
+    fresh = Renderer()
+    sc = S.cornell_spheres()
+    with pytest.raises(TrtError):                     # no scene yet
+        fresh.render(S.params_for(sc, width=8, spp=1))
+    fresh.scene_set(sc)
+    with pytest.raises(TrtError):                     # W-1 == 0 divides by zero in main.c:265
+        fresh.render(S.RenderParams(width=1, height=1, spp=1, bounces=1, cam=sc.camera()))
+    with pytest.raises(TrtError):
+        fresh.render(S.params_for(sc, width=8, spp=0))
+    # smallest legal image, one sample, zero bounces: black radiance, AOVs untouched (loop never runs)
+    r = fresh.render(S.RenderParams(width=2, height=2, spp=1, bounces=0, cam=sc.camera()))
+    assert not r["canva"].any() and not r["albedo"].any()
+    # ragged sizes: not a multiple of the 8x4 tile, spp not a multiple of the chunk
+    rp = S.params_for(sc, width=61, spp=37)
+    g = fresh.render(rp)
+    o = oracle.render(sc, rp, rng=RNG_PHILOX)
+    assert (np.abs(g["canva"] - o["canva"]).max(axis=1) <= 1).mean() > 0.97
+    # empty scene: every ray misses
+    empty = S.Scene(name="empty", spheres=np.zeros(0, S.SPHERE), triangles=np.zeros(0, S.TRIANGLE), mat_list=np.zeros(0, S.MATERIAL))
+    fresh.scene_set(empty)
+    r = fresh.render(S.RenderParams(width=16, height=8, spp=2, bounces=3, cam=sc.camera()))
+    assert not r["canva"].any() and r["stats"]["rays"] == 16 * 8 * 2
+    fresh.close()

@@ -1,0 +1,590 @@
+// api.cu — the C ABI of libtipe_rt.so (include/tipe_rt.h): context, scene upload, the render call
+// that replaces main.c:402-453, and the device-resident pieces it is made of.
+//
+// Host logic only; every kernel lives in pathtrace.cu / primary.cu / bvh_build.cu / kat.cu.
+// There is no CPU rendering path in this library: no device => trt_init fails.
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tipe_rt.h"
+#include "trt_kernels.h"
+
+namespace {
+
+thread_local std::string g_init_error;
+
+struct DeviceCtx {
+    int dev = 0;
+    int n_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
+    // scene
+    double* sph_raw = nullptr; double* tri_raw = nullptr; int* quel_mat = nullptr;
+    float4 *sph = nullptr, *sph_mat = nullptr, *tri = nullptr, *tri_uv = nullptr, *nodes = nullptr, *texels = nullptr;
+    int* tri_orig = nullptr;
+    DevScene scene{};
+    // work buffers
+    unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
+    unsigned long long* h_ctrs = nullptr;      // pinned mirror
+    long long* accum = nullptr; size_t accum_px = 0;
+    double* out = nullptr; size_t out_px = 0;  // canva | albedo | normal, each [npix][3]
+};
+
+}  // namespace
+
+struct trt_ctx {
+    std::vector<DeviceCtx> devs;
+    std::string err;
+    bool has_scene = false;
+    trt_bvh_info info{};
+};
+
+namespace {
+
+int fail(trt_ctx* ctx, int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_init_error = buf;
+    return code;
+}
+
+#define CU(ctx, call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? TRT_ERR_OOM : TRT_ERR_CUDA,          \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+void free_scene(DeviceCtx& d)
+{
+    cudaSetDevice(d.dev);
+    void* ptrs[] = {d.sph_raw, d.tri_raw, d.quel_mat, d.sph, d.sph_mat, d.tri, d.tri_uv, d.nodes, d.texels, d.tri_orig};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    d.sph_raw = d.tri_raw = nullptr; d.quel_mat = nullptr;
+    d.sph = d.sph_mat = d.tri = d.tri_uv = d.nodes = d.texels = nullptr; d.tri_orig = nullptr;
+    d.scene = DevScene{};
+}
+
+int ensure_accum(trt_ctx* ctx, DeviceCtx& d, size_t npix)
+{
+    if (d.accum_px >= npix) return TRT_OK;
+    if (d.accum) cudaFree(d.accum);
+    d.accum = nullptr; d.accum_px = 0;
+    CU(ctx, cudaMalloc(&d.accum, sizeof(long long) * 9 * npix));
+    d.accum_px = npix;
+    return TRT_OK;
+}
+
+int ensure_out(trt_ctx* ctx, DeviceCtx& d, size_t npix)
+{
+    if (d.out_px >= npix) return TRT_OK;
+    if (d.out) cudaFree(d.out);
+    d.out = nullptr; d.out_px = 0;
+    CU(ctx, cudaMalloc(&d.out, sizeof(double) * 9 * npix));
+    d.out_px = npix;
+    return TRT_OK;
+}
+
+int check_params(trt_ctx* ctx, const trt_params* p)
+{
+    if (!ctx) return TRT_ERR_INVALID;
+    if (!p) return fail(ctx, TRT_ERR_INVALID, "params is NULL");
+    if (p->largeur_image < 2 || p->hauteur_image < 2) return fail(ctx, TRT_ERR_INVALID, "image must be at least 2x2 (u = i/(W-1), main.c:265)");
+    if ((long long)p->largeur_image * p->hauteur_image > (1LL << 30)) return fail(ctx, TRT_ERR_INVALID, "image too large");
+    if (p->nbRayonParPixel < 1) return fail(ctx, TRT_ERR_INVALID, "nbRayonParPixel must be >= 1");
+    if (p->nbRebondMax < 0) return fail(ctx, TRT_ERR_INVALID, "nbRebondMax must be >= 0");
+    if (p->sample_offset < 0 || p->sample_total < 0) return fail(ctx, TRT_ERR_INVALID, "negative sample_offset / sample_total");
+    if (!ctx->has_scene) return fail(ctx, TRT_ERR_NO_SCENE, "trt_scene_set has not been called");
+    return TRT_OK;
+}
+
+// Launches K2 for `spp` samples starting at global sample `offset` into `accum` on device d.
+int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int offset, long long* accum)
+{
+    RenderArgs A{};
+    A.scene = d.scene;
+    A.W = p->largeur_image; A.H = p->hauteur_image;
+    A.spp = spp; A.sample_offset = offset;
+    A.bounces = p->nbRebondMax;
+    A.use_ao = p->useAO ? 1 : 0;
+    A.inv_ao = (float)(1.0 / p->AO_intensity);
+    A.emit_scale_ao = (float)(1.5 * p->AO_intensity);
+    A.focus = (float)p->focus_distance;
+    A.aperture_x = (float)p->ouverture_x; A.aperture_y = (float)p->ouverture_y;
+    A.inv_wm1 = (float)(1.0 / (double)(A.W - 1)); A.inv_hm1 = (float)(1.0 / (double)(A.H - 1));
+    const trt_camera& c = p->cam;
+    A.cam_origin = make_float3((float)c.origin.e[0], (float)c.origin.e[1], (float)c.origin.e[2]);
+    A.cam_hor = make_float3((float)c.horizontal.e[0], (float)c.horizontal.e[1], (float)c.horizontal.e[2]);
+    A.cam_ver = make_float3((float)c.vertical.e[0], (float)c.vertical.e[1], (float)c.vertical.e[2]);
+    A.cam_corner = make_float3((float)(c.coin_bas_gauche.e[0] - c.origin.e[0]), (float)(c.coin_bas_gauche.e[1] - c.origin.e[1]),
+                               (float)(c.coin_bas_gauche.e[2] - c.origin.e[2]));
+    A.key0 = (uint32_t)(p->seed & 0xffffffffu); A.key1 = (uint32_t)(p->seed >> 32);
+    A.chunk = spp < 32 ? spp : 32;
+    A.n_chunks = (spp + A.chunk - 1) / A.chunk;
+    A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;
+    A.n_items = (long long)A.tiles_x * A.tiles_y * A.n_chunks * 32;
+    A.item_counter = d.ctrs;
+    A.counters = d.ctrs + 1;
+    A.accum = accum;
+    CU(ctx, cudaMemsetAsync(d.ctrs, 0, sizeof(unsigned long long) * 8, d.stream));
+    CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+    CU(ctx, trt_launch_pathtrace(A, d.n_sms, (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, (p->flags & TRT_FLAG_COUNT_TESTS) != 0, d.stream));
+    CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, d.stream));
+    return TRT_OK;
+}
+
+void collect_stats(trt_ctx* ctx, const trt_params* p, trt_stats* st, bool traced)
+{
+    if (!st) return;
+    if (traced) {
+        st->rays = st->box_tests = st->tri_tests = st->sphere_tests = 0;
+        st->ms_trace = 0.0;
+        for (auto& d : ctx->devs) {
+            float ms = 0.0f;
+            cudaSetDevice(d.dev);
+            if (cudaEventElapsedTime(&ms, d.ev_a, d.ev_b) == cudaSuccess && ms > st->ms_trace) st->ms_trace = ms;
+            st->rays += d.h_ctrs[1]; st->box_tests += d.h_ctrs[2]; st->tri_tests += d.h_ctrs[3]; st->sphere_tests += d.h_ctrs[4];
+        }
+        st->paths = (uint64_t)p->largeur_image * (uint64_t)p->hauteur_image * (uint64_t)p->nbRayonParPixel;
+    }
+}
+
+double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+TRT_API int trt_version(void) { return 100; }
+
+TRT_API const char* trt_last_error(const trt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_error.c_str(); }
+
+TRT_API int trt_default_overrides(trt_mat_override* out, int capacity)
+{
+    if (!out || capacity < 3) return 3;
+    memset(out, 0, sizeof(trt_mat_override) * 3);
+    out[0].material_ordinal = 1; out[0].mask = TRT_OV_EMISSION_COLOR | TRT_OV_EMISSION_STRENGTH | TRT_OV_ALPHA;
+    out[0].emissionColor[0] = out[0].emissionColor[1] = out[0].emissionColor[2] = 1.0;
+    out[0].emissionStrength = 1.85; out[0].alpha = 1.0;
+    out[1].material_ordinal = 4; out[1].mask = TRT_OV_ALPHA | TRT_OV_MATERIAL_INDEX | TRT_OV_REFLECTION;
+    out[1].alpha = 0.6; out[1].materialIndex = 1.33; out[1].reflectionStrength = 0.93;
+    out[2].material_ordinal = 3; out[2].mask = TRT_OV_ALPHA | TRT_OV_MATERIAL_INDEX | TRT_OV_REFLECTION;
+    out[2].alpha = 0.1; out[2].materialIndex = 1.50; out[2].reflectionStrength = 0.3;
+    return 3;
+}
+
+TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
+{
+    if (!out) return fail(nullptr, TRT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, TRT_ERR_NO_DEVICE, "no CUDA device (%s); libtipe_rt has no CPU fallback", cudaGetErrorString(e));
+    if (n_devices < 1) n_devices = 1;
+    if (n_devices > TRT_MAX_RESOLVE_SOURCES) return fail(nullptr, TRT_ERR_INVALID, "at most %d devices", TRT_MAX_RESOLVE_SOURCES);
+    trt_ctx* ctx = new trt_ctx();
+    for (int k = 0; k < n_devices; k++) {
+        DeviceCtx d;
+        d.dev = device_ids ? device_ids[k] : k;
+        if (d.dev < 0 || d.dev >= count) { delete ctx; return fail(nullptr, TRT_ERR_NO_DEVICE, "device %d not present (%d visible)", d.dev, count); }
+        ctx->devs.push_back(d);
+    }
+    for (auto& d : ctx->devs) {
+        cudaDeviceProp prop;
+        if ((e = cudaSetDevice(d.dev)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, d.dev)) != cudaSuccess ||
+            (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.ev_a)) != cudaSuccess || (e = cudaEventCreate(&d.ev_b)) != cudaSuccess ||
+            (e = cudaEventCreate(&d.ev_c)) != cudaSuccess || (e = cudaEventCreate(&d.ev_d)) != cudaSuccess ||
+            (e = cudaMalloc(&d.ctrs, sizeof(unsigned long long) * 8)) != cudaSuccess ||
+            (e = cudaMallocHost(&d.h_ctrs, sizeof(unsigned long long) * 8)) != cudaSuccess) {
+            fail(nullptr, TRT_ERR_CUDA, "device %d set-up failed: %s", d.dev, cudaGetErrorString(e));
+            trt_destroy(ctx);
+            return TRT_ERR_CUDA;
+        }
+        if (prop.major < 10) {
+            fail(nullptr, TRT_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", d.dev, prop.major, prop.minor);
+            trt_destroy(ctx);
+            return TRT_ERR_NO_DEVICE;
+        }
+        d.n_sms = prop.multiProcessorCount;
+        memset(d.h_ctrs, 0, sizeof(unsigned long long) * 8);
+    }
+    // peer access root <- others, for the fused reduce+resolve
+    for (size_t k = 1; k < ctx->devs.size(); k++) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[k].dev);
+        if (!can) { fail(nullptr, TRT_ERR_CUDA, "device %d cannot map device %d's memory (no NVLink/P2P)", ctx->devs[0].dev, ctx->devs[k].dev); trt_destroy(ctx); return TRT_ERR_CUDA; }
+        cudaSetDevice(ctx->devs[0].dev);
+        e = cudaDeviceEnablePeerAccess(ctx->devs[k].dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { fail(nullptr, TRT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); trt_destroy(ctx); return TRT_ERR_CUDA; }
+        cudaGetLastError();
+    }
+    *out = ctx;
+    return TRT_OK;
+}
+
+TRT_API void trt_destroy(trt_ctx* ctx)
+{
+    if (!ctx) return;
+    for (auto& d : ctx->devs) {
+        cudaSetDevice(d.dev);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        free_scene(d);
+        if (d.accum) cudaFree(d.accum);
+        if (d.out) cudaFree(d.out);
+        if (d.ctrs) cudaFree(d.ctrs);
+        if (d.h_ctrs) cudaFreeHost(d.h_ctrs);
+        cudaEvent_t evs[] = {d.ev_a, d.ev_b, d.ev_c, d.ev_d};
+        for (cudaEvent_t ev : evs) if (ev) cudaEventDestroy(ev);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+TRT_API void* trt_stream(trt_ctx* ctx) { return ctx && !ctx->devs.empty() ? (void*)ctx->devs[0].stream : nullptr; }
+
+TRT_API int trt_synchronize(trt_ctx* ctx)
+{
+    if (!ctx) return TRT_ERR_INVALID;
+    for (auto& d : ctx->devs) { CU(ctx, cudaSetDevice(d.dev)); CU(ctx, cudaStreamSynchronize(d.stream)); }
+    return TRT_OK;
+}
+
+TRT_API int trt_scene_set(trt_ctx* ctx,
+                          const trt_sphere* sphere_list, int nbSpheres,
+                          const trt_triangle* triangle_list, int nbTriangles,
+                          const trt_material* mat_list, int tex_width, int tex_height, int nbMaterials,
+                          const int* quelMatPourTri,
+                          const trt_mat_override* overrides, int n_overrides)
+{
+    if (!ctx) return TRT_ERR_INVALID;
+    if (nbSpheres < 0 || nbTriangles < 0) return fail(ctx, TRT_ERR_INVALID, "negative primitive count");
+    if (nbSpheres > 0 && !sphere_list) return fail(ctx, TRT_ERR_INVALID, "sphere_list is NULL");
+    if (nbSpheres > TRT_MAX_SMEM_SPHERES) return fail(ctx, TRT_ERR_INVALID, "at most %d spheres (they live in shared memory)", TRT_MAX_SMEM_SPHERES);
+    if (nbTriangles > 0) {
+        if (!triangle_list || !quelMatPourTri) return fail(ctx, TRT_ERR_INVALID, "triangle_list / quelMatPourTri is NULL");
+        if (!mat_list || tex_width < 1 || tex_height < 1 || nbMaterials < 1)
+            return fail(ctx, TRT_ERR_INVALID, "triangles need mat_list (the reference textures every triangle, main.c:86)");
+        for (int k = 0; k < nbTriangles; k++)
+            if (quelMatPourTri[k] < 0 || quelMatPourTri[k] >= nbMaterials)
+                return fail(ctx, TRT_ERR_INVALID, "quelMatPourTri[%d] = %d outside 0..%d", k, quelMatPourTri[k], nbMaterials - 1);
+    } else { tex_width = tex_height = nbMaterials = 0; }
+
+    trt_mat_override builtin[3];
+    if (!overrides && n_overrides < 0) { n_overrides = trt_default_overrides(builtin, 3); overrides = builtin; }
+    if (n_overrides < 0 || (n_overrides > 0 && !overrides)) return fail(ctx, TRT_ERR_INVALID, "bad overrides");
+
+    const size_t n_texels = (size_t)nbMaterials * (size_t)tex_width * (size_t)tex_height;
+    ctx->has_scene = false;
+    const double t0 = now_ms();
+    for (auto& d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.dev));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        free_scene(d);
+        double *mats_raw = nullptr, *ov_raw = nullptr;
+        const size_t ns = (size_t)(nbSpheres > 0 ? nbSpheres : 1), nt = (size_t)(nbTriangles > 0 ? nbTriangles : 1);
+        CU(ctx, cudaMalloc(&d.sph_raw, sizeof(trt_sphere) * ns));
+        CU(ctx, cudaMalloc(&d.sph, sizeof(float4) * ns));
+        CU(ctx, cudaMalloc(&d.sph_mat, sizeof(float4) * 3 * ns));
+        CU(ctx, cudaMalloc(&d.tri_raw, sizeof(trt_triangle) * nt));
+        CU(ctx, cudaMalloc(&d.quel_mat, sizeof(int) * nt));
+        CU(ctx, cudaMalloc(&d.tri, sizeof(float4) * 3 * nt));
+        CU(ctx, cudaMalloc(&d.tri_uv, sizeof(float4) * 2 * nt));
+        CU(ctx, cudaMalloc(&d.tri_orig, sizeof(int) * nt));
+        CU(ctx, cudaMalloc(&d.nodes, sizeof(float4) * 4 * nt));
+        CU(ctx, cudaMalloc(&d.texels, sizeof(float4) * 3 * (n_texels > 0 ? n_texels : 1)));
+        if (nbSpheres) CU(ctx, cudaMemcpyAsync(d.sph_raw, sphere_list, sizeof(trt_sphere) * nbSpheres, cudaMemcpyHostToDevice, d.stream));
+        if (nbTriangles) {
+            CU(ctx, cudaMemcpyAsync(d.tri_raw, triangle_list, sizeof(trt_triangle) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaMemcpyAsync(d.quel_mat, quelMatPourTri, sizeof(int) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaMalloc(&mats_raw, sizeof(trt_material) * n_texels));
+            cudaError_t e = cudaMemcpyAsync(mats_raw, mat_list, sizeof(trt_material) * n_texels, cudaMemcpyHostToDevice, d.stream);
+            if (e == cudaSuccess && n_overrides > 0) {
+                e = cudaMalloc(&ov_raw, sizeof(trt_mat_override) * n_overrides);
+                if (e == cudaSuccess) e = cudaMemcpyAsync(ov_raw, overrides, sizeof(trt_mat_override) * n_overrides, cudaMemcpyHostToDevice, d.stream);
+            }
+            if (e != cudaSuccess) { cudaFree(mats_raw); if (ov_raw) cudaFree(ov_raw); CU(ctx, e); }
+        }
+        BuildInputs in{};
+        in.spheres_raw = d.sph_raw; in.n_spheres = nbSpheres;
+        in.tris_raw = d.tri_raw; in.n_tris = nbTriangles;
+        in.mats_raw = mats_raw; in.tex_w = tex_width; in.tex_h = tex_height; in.n_materials = nbMaterials;
+        in.quel_mat = d.quel_mat; in.overrides_raw = ov_raw; in.n_overrides = nbTriangles ? n_overrides : 0;
+        BuildOutputs bo{};
+        bo.sph = d.sph; bo.sph_mat = d.sph_mat; bo.tri = d.tri; bo.tri_uv = d.tri_uv; bo.tri_orig = d.tri_orig;
+        bo.nodes = d.nodes; bo.texels = d.texels;
+        cudaError_t e = trt_build_scene(in, bo, d.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+        if (mats_raw) cudaFree(mats_raw);
+        if (ov_raw) cudaFree(ov_raw);
+        CU(ctx, e);
+        DevScene& s = d.scene;
+        s.n_spheres = nbSpheres; s.sph = d.sph; s.sph_mat = d.sph_mat; s.sph64 = d.sph_raw;
+        s.n_tris = nbTriangles; s.tri = d.tri; s.tri_uv = d.tri_uv; s.tri_orig = d.tri_orig; s.tri64 = d.tri_raw;
+        s.quel_mat = d.quel_mat; s.nodes = d.nodes; s.root = bo.root;
+        s.texels = d.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
+        s.tri_tmin = bo.tri_tmin;
+        if (&d == &ctx->devs[0]) {
+            ctx->info.n_nodes = nbTriangles > 1 ? nbTriangles - 1 : 0;
+            ctx->info.n_leaves = nbTriangles;
+            ctx->info.max_depth = bo.max_depth; ctx->info.n_twins = bo.n_twins; ctx->info.sah_cost = bo.sah_cost;
+        }
+    }
+    ctx->info.ms_build = now_ms() - t0;
+    ctx->has_scene = true;
+    return TRT_OK;
+}
+
+TRT_API int trt_bvh_info_get(trt_ctx* ctx, trt_bvh_info* out)
+{
+    if (!ctx || !out) return TRT_ERR_INVALID;
+    if (!ctx->has_scene) return fail(ctx, TRT_ERR_NO_SCENE, "trt_scene_set has not been called");
+    *out = ctx->info;
+    return TRT_OK;
+}
+
+TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_accum, trt_stats* stats)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    if (!d_accum) return fail(ctx, TRT_ERR_INVALID, "d_accum is NULL");
+    if (ctx->devs.size() != 1) return fail(ctx, TRT_ERR_INVALID, "trt_accumulate works on a single-device ctx (one process per GPU); use trt_render for in-process multi-GPU");
+    const double t0 = now_ms();
+    DeviceCtx& d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.dev));
+    rc = launch_trace(ctx, d, params, params->nbRayonParPixel, params->sample_offset, (long long*)d_accum);
+    if (rc != TRT_OK) return rc;
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        collect_stats(ctx, params, stats, true);
+        stats->kernel_launches = 1;
+        stats->ms_total = now_ms() - t0;
+    }
+    return TRT_OK;
+}
+
+static int resolve_common(trt_ctx* ctx, const trt_params* p, const long long* const* srcs, int n_src,
+                          double* d_canva, double* d_albedo, double* d_normal)
+{
+    DeviceCtx& d = ctx->devs[0];
+    ResolveArgs R{};
+    R.W = p->largeur_image; R.H = p->hauteur_image;
+    R.divisor = p->sample_total > 0 ? p->sample_total : p->nbRayonParPixel;
+    R.n_src = n_src;
+    for (int k = 0; k < n_src; k++) R.src[k] = srcs[k];
+    R.canva = d_canva; R.albedo = d_albedo; R.normal = d_normal;
+    CU(ctx, trt_launch_resolve(R, d.n_sms, d.stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_resolve_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                               double* d_canva, double* d_albedo, double* d_normal)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    if (!d_accum || !d_canva || !d_albedo || !d_normal) return fail(ctx, TRT_ERR_INVALID, "NULL device buffer");
+    CU(ctx, cudaSetDevice(ctx->devs[0].dev));
+    const long long* src = (const long long*)d_accum;
+    rc = resolve_common(ctx, params, &src, 1, d_canva, d_albedo, d_normal);
+    if (rc != TRT_OK) return rc;
+    CU(ctx, cudaStreamSynchronize(ctx->devs[0].stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                        trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    if (!d_accum) return fail(ctx, TRT_ERR_INVALID, "d_accum is NULL");
+    DeviceCtx& d = ctx->devs[0];
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    CU(ctx, cudaSetDevice(d.dev));
+    if ((rc = ensure_out(ctx, d, npix)) != TRT_OK) return rc;
+    const long long* src = (const long long*)d_accum;
+    rc = resolve_common(ctx, params, &src, 1, d.out, d.out + 3 * npix, d.out + 6 * npix);
+    if (rc != TRT_OK) return rc;
+    if (canva) CU(ctx, cudaMemcpyAsync(canva, d.out, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+    if (albedo_tab) CU(ctx, cudaMemcpyAsync(albedo_tab, d.out + 3 * npix, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+    if (normal_tab) CU(ctx, cudaMemcpyAsync(normal_tab, d.out + 6 * npix, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
+                       trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    const double t0 = now_ms();
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    const int n_dev = (int)ctx->devs.size();
+    const int spp = params->nbRayonParPixel;
+    int launches = 0;
+
+    // spp split: device k renders samples [k*spp/N, (k+1)*spp/N) of every pixel
+    std::vector<const long long*> srcs;
+    for (int k = 0; k < n_dev; k++) {
+        DeviceCtx& d = ctx->devs[k];
+        const int s0 = (int)((long long)spp * k / n_dev), s1 = (int)((long long)spp * (k + 1) / n_dev);
+        CU(ctx, cudaSetDevice(d.dev));
+        if ((rc = ensure_accum(ctx, d, npix)) != TRT_OK) return rc;
+        CU(ctx, cudaMemsetAsync(d.accum, 0, sizeof(long long) * 9 * npix, d.stream));
+        if (s1 > s0) {
+            if ((rc = launch_trace(ctx, d, params, s1 - s0, params->sample_offset + s0, d.accum)) != TRT_OK) return rc;
+            launches++;
+        } else {
+            CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+            CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+            memset(d.h_ctrs, 0, sizeof(unsigned long long) * 8);
+        }
+        CU(ctx, cudaEventRecord(d.ev_c, d.stream));
+        srcs.push_back(d.accum);
+    }
+    // root: wait for the peers, then reduce over NVLink peer mappings while tonemapping
+    DeviceCtx& root = ctx->devs[0];
+    CU(ctx, cudaSetDevice(root.dev));
+    if ((rc = ensure_out(ctx, root, npix)) != TRT_OK) return rc;
+    for (int k = 1; k < n_dev; k++) CU(ctx, cudaStreamWaitEvent(root.stream, ctx->devs[k].ev_c, 0));
+    trt_params rp = *params;
+    if (rp.sample_total <= 0) rp.sample_total = spp;
+    if ((rc = resolve_common(ctx, &rp, srcs.data(), n_dev, root.out, root.out + 3 * npix, root.out + 6 * npix)) != TRT_OK) return rc;
+    launches++;
+    CU(ctx, cudaEventRecord(root.ev_d, root.stream));
+    if (canva) CU(ctx, cudaMemcpyAsync(canva, root.out, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, root.stream));
+    if (albedo_tab) CU(ctx, cudaMemcpyAsync(albedo_tab, root.out + 3 * npix, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, root.stream));
+    if (normal_tab) CU(ctx, cudaMemcpyAsync(normal_tab, root.out + 6 * npix, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, root.stream));
+    const double t_sync0 = now_ms();
+    for (auto& d : ctx->devs) { CU(ctx, cudaSetDevice(d.dev)); CU(ctx, cudaStreamSynchronize(d.stream)); }
+    (void)t_sync0;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        collect_stats(ctx, params, stats, true);
+        float ms = 0.0f;
+        cudaSetDevice(root.dev);
+        if (cudaEventElapsedTime(&ms, root.ev_c, root.ev_d) == cudaSuccess) stats->ms_reduce_resolve = ms;
+        stats->kernel_launches = launches;
+        stats->ms_total = now_ms() - t0;
+        stats->ms_d2h = stats->ms_total - stats->ms_trace - stats->ms_reduce_resolve;
+        if (stats->ms_d2h < 0) stats->ms_d2h = 0;
+    }
+    return TRT_OK;
+}
+
+TRT_API int trt_primary(trt_ctx* ctx, const trt_params* params, double* t, int* id, trt_vec3* normal, trt_vec3* albedo)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    DeviceCtx& d = ctx->devs[0];
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    CU(ctx, cudaSetDevice(d.dev));
+    double* buf = nullptr;                    // t | normal | albedo | id
+    CU(ctx, cudaMalloc(&buf, sizeof(double) * 8 * npix));
+    PrimaryArgs P{};
+    P.scene = d.scene; P.W = params->largeur_image; P.H = params->hauteur_image;
+    P.focus = params->focus_distance;
+    memcpy(P.cam, &params->cam, sizeof(double) * 12);
+    P.t = buf; P.normal = buf + npix; P.albedo = buf + 4 * npix; P.id = (int*)(buf + 7 * npix);
+    cudaError_t e = trt_launch_primary(P, d.stream);
+    if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, P.t, sizeof(double) * npix, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && normal) e = cudaMemcpyAsync(normal, P.normal, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && albedo) e = cudaMemcpyAsync(albedo, P.albedo, sizeof(double) * 3 * npix, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, P.id, sizeof(int) * npix, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(buf);
+    CU(ctx, e);
+    return TRT_OK;
+}
+
+// ---- known-answer entry points ---------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+#define KAT_BEGIN                                                   \
+    if (!ctx) return TRT_ERR_INVALID;                               \
+    if (n < 0) return fail(ctx, TRT_ERR_INVALID, "n < 0");          \
+    if (n == 0) return TRT_OK;                                      \
+    DeviceCtx& d = ctx->devs[0];                                    \
+    CU(ctx, cudaSetDevice(d.dev));
+#define UP(buf, src, bytes) CU(ctx, buf.alloc(bytes)); CU(ctx, cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, d.stream))
+#define OUTBUF(buf, bytes) CU(ctx, buf.alloc(bytes))
+#define DOWN(dst, buf, bytes) CU(ctx, cudaMemcpyAsync(dst, buf.p, bytes, cudaMemcpyDeviceToHost, d.stream))
+
+TRT_API int trt_kat_hit_sphere(trt_ctx* ctx, int n, const float* cr, const float* ray, int* hit, float* dst, float* point, float* normal)
+{
+    KAT_BEGIN
+    DevBuf a, b, h, t, p, q;
+    UP(a, cr, sizeof(float) * 4 * n); UP(b, ray, sizeof(float) * 6 * n);
+    OUTBUF(h, sizeof(int) * n); OUTBUF(t, sizeof(float) * n); OUTBUF(p, sizeof(float) * 3 * n); OUTBUF(q, sizeof(float) * 3 * n);
+    CU(ctx, trt_kat_launch_sphere(n, (const float4*)a.p, (const float*)b.p, (int*)h.p, (float*)t.p, (float*)p.p, (float*)q.p, d.stream));
+    DOWN(hit, h, sizeof(int) * n); DOWN(dst, t, sizeof(float) * n); DOWN(point, p, sizeof(float) * 3 * n); DOWN(normal, q, sizeof(float) * 3 * n);
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_kat_hit_triangle(trt_ctx* ctx, int n, const float* abc, const float* ray, int* hit, float* dst_u_v)
+{
+    KAT_BEGIN
+    DevBuf a, b, h, t;
+    UP(a, abc, sizeof(float) * 9 * n); UP(b, ray, sizeof(float) * 6 * n);
+    OUTBUF(h, sizeof(int) * n); OUTBUF(t, sizeof(float) * 3 * n);
+    CU(ctx, trt_kat_launch_triangle(n, (const float*)a.p, (const float*)b.p, (int*)h.p, (float*)t.p, d.stream));
+    DOWN(hit, h, sizeof(int) * n); DOWN(dst_u_v, t, sizeof(float) * 3 * n);
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_kat_refract(trt_ctx* ctx, int n, const float* in8, float* out)
+{
+    KAT_BEGIN
+    DevBuf a, o;
+    UP(a, in8, sizeof(float) * 8 * n); OUTBUF(o, sizeof(float) * 3 * n);
+    CU(ctx, trt_kat_launch_refract(n, (const float*)a.p, (float*)o.p, d.stream));
+    DOWN(out, o, sizeof(float) * 3 * n);
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_kat_philox(trt_ctx* ctx, int n, const uint32_t* ctr_key, uint32_t* out)
+{
+    KAT_BEGIN
+    DevBuf a, o;
+    UP(a, ctr_key, sizeof(uint32_t) * 6 * n); OUTBUF(o, sizeof(uint32_t) * 4 * n);
+    CU(ctx, trt_kat_launch_philox(n, (const uint32_t*)a.p, (uint32_t*)o.p, d.stream));
+    DOWN(out, o, sizeof(uint32_t) * 4 * n);
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
+TRT_API int trt_kat_tonemap(trt_ctx* ctx, int n, const int64_t* sums, int spp, double* out)
+{
+    KAT_BEGIN
+    if (spp < 1) return fail(ctx, TRT_ERR_INVALID, "spp < 1");
+    DevBuf a, o;
+    UP(a, sums, sizeof(int64_t) * n); OUTBUF(o, sizeof(double) * n);
+    CU(ctx, trt_kat_launch_tonemap(n, (const long long*)a.p, spp, (double*)o.p, d.stream));
+    DOWN(out, o, sizeof(double) * n);
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
+}  // extern "C"

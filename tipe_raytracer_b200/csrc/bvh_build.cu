@@ -1,0 +1,371 @@
+// bvh_build.cu — K3: scene conversion (FP64 AoS -> device layout) and the GPU LBVH build.
+//
+// The reference has no acceleration structure (closest_hit scans every triangle, main.c:81-90);
+// this is new.  Input = the caller's arrays exactly as main.c holds them (sphere[] 112 B,
+// triangle[] 200 B, material[] 80 B per texel), already copied to the device.  Output = the
+// DevScene layout of trt_device.cuh.
+//
+//   1. tri_bounds      per-triangle FP32 box (rounded outward) + centroid; scene bounds by atomics
+//   2. morton_keys     36-bit Morton code of the centroid << 28 | triangle index  (unique 64-bit keys)
+//   3. radix sort      cub::DeviceRadixSort (library; the build is not on the per-ray path)
+//   4. emit_leaves     triangles re-laid out in sorted (leaf) order: A, AB, AC, N as 3 float4 (48 B)
+//   5. find_twins      coincident opposite-facing triangles ("doubleface" meshes) share a Morton code and
+//                      are neighbours after the sort; each records the other's leaf position
+//   6. build_hierarchy Karras 2012: one thread per internal node, longest-common-prefix ranges
+//   7. refit           bottom-up boxes, second arriver at each node continues (atomic flags)
+//   8. write_nodes     64-byte nodes with both child boxes inline + SAH cost reduction
+#include <cub/device/device_radix_sort.cuh>
+
+#include "trt_kernels.h"
+
+namespace {
+
+constexpr int IDX_BITS = 28;                        // up to 2^28 triangles
+constexpr unsigned long long IDX_MASK = (1ULL << IDX_BITS) - 1ULL;
+
+struct MatOverrideDev { int ordinal; unsigned mask; double ec[3]; double es, rs, alpha, index; };
+static_assert(sizeof(MatOverrideDev) == 64, "mirror of trt_mat_override");
+
+// ---- ordered-int encoding so float min/max can use integer atomics ------------------------------
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void convert_spheres(const double* __restrict__ raw, int n, float4* sph, float4* mat)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* s = raw + 14 * (size_t)k;      // center[3], radius, diffuse[3], emission[3], es, rs, alpha, index
+    sph[k] = make_float4((float)s[0], (float)s[1], (float)s[2], (float)s[3]);
+    mat[3 * k + 0] = make_float4((float)s[4], (float)s[5], (float)s[6], (float)s[12]);
+    mat[3 * k + 1] = make_float4((float)s[7], (float)s[8], (float)s[9], (float)s[10]);
+    mat[3 * k + 2] = make_float4((float)s[11], (float)s[13], 0.0f, 0.0f);
+}
+
+// material[] slab -> texel records, with the per-ordinal overrides of texture.h:71-87 baked in.
+__global__ void convert_texels(const double* __restrict__ raw, size_t n_texels, int texels_per_mat,
+                               const MatOverrideDev* __restrict__ ov, int n_ov, float4* out)
+{
+    for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_texels; t += (size_t)gridDim.x * blockDim.x) {
+        const double* m = raw + 10 * t;
+        double dr = m[0], dg = m[1], db = m[2], er = m[3], eg = m[4], eb = m[5], es = m[6], rs = m[7], al = m[8], ix = m[9];
+        const int ordinal = (int)(t / (size_t)texels_per_mat);
+        for (int k = 0; k < n_ov; k++) {
+            if (ov[k].ordinal != ordinal) continue;
+            const unsigned mask = ov[k].mask;
+            if (mask & 1u) { er = ov[k].ec[0]; eg = ov[k].ec[1]; eb = ov[k].ec[2]; }
+            if (mask & 2u) es = ov[k].es;
+            if (mask & 4u) rs = ov[k].rs;
+            if (mask & 8u) al = ov[k].alpha;
+            if (mask & 16u) ix = ov[k].index;
+        }
+        out[3 * t + 0] = make_float4((float)dr, (float)dg, (float)db, (float)al);
+        out[3 * t + 1] = make_float4((float)er, (float)eg, (float)eb, (float)es);
+        out[3 * t + 2] = make_float4((float)rs, (float)ix, 0.0f, 0.0f);
+    }
+}
+
+// bounds[0..2] = ordered-int min, [3..5] = ordered-int max, [6] = ordered-int max |coord|
+__global__ void tri_bounds(const double* __restrict__ raw, int n, float4* box_lo, float4* box_hi, int* bounds)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    float cen[3] = {0, 0, 0};
+    if (k < n) {
+        const double* t = raw + 25 * (size_t)k;
+        for (int a = 0; a < 3; a++) {
+            const double mn = fmin(t[a], fmin(t[3 + a], t[6 + a])), mx = fmax(t[a], fmax(t[3 + a], t[6 + a]));
+            lo[a] = __double2float_rd(mn); hi[a] = __double2float_ru(mx);
+            cen[a] = (float)((t[a] + t[3 + a] + t[6 + a]) * (1.0 / 3.0));
+        }
+        box_lo[k] = make_float4(lo[0], lo[1], lo[2], cen[0]);
+        box_hi[k] = make_float4(hi[0], hi[1], hi[2], cen[1]);
+    }
+    // warp-reduce then one atomic per warp
+    float amax = fmaxf(fmaxf(fmaxf(fabsf(lo[0]), fabsf(hi[0])), fmaxf(fabsf(lo[1]), fabsf(hi[1]))), fmaxf(fabsf(lo[2]), fabsf(hi[2])));
+    if (k >= n) amax = 0.0f;
+    for (int off = 16; off > 0; off >>= 1) {
+        for (int a = 0; a < 3; a++) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], off));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], off));
+        }
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int a = 0; a < 3; a++) { atomicMin(bounds + a, f2ord(lo[a])); atomicMax(bounds + 3 + a, f2ord(hi[a])); }
+        atomicMax(bounds + 6, f2ord(amax));
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread3(unsigned v)     // bit k of v -> bit 3k
+{
+    unsigned long long x = v & 0x1fffffu;
+    x = (x | (x << 32)) & 0x001f00000000ffffULL;
+    x = (x | (x << 16)) & 0x001f0000ff0000ffULL;
+    x = (x | (x << 8)) & 0x100f00f00f00f00fULL;
+    x = (x | (x << 4)) & 0x10c30c30c30c30c3ULL;
+    x = (x | (x << 2)) & 0x1249249249249249ULL;
+    return x;
+}
+
+__global__ void morton_keys(int n, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                            const int* __restrict__ bounds, unsigned long long* keys)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const float4 lo = box_lo[k], hi = box_hi[k];
+    const float cx = lo.w, cy = hi.w, cz = 0.5f * (lo.z + hi.z);   // x,y centroid exact; z: box centre
+    float q[3];
+    const float c[3] = {cx, cy, cz};
+    for (int a = 0; a < 3; a++) {
+        const float mn = ord2f(bounds[a]), mx = ord2f(bounds[3 + a]);
+        const float ext = fmaxf(mx - mn, 1e-30f);
+        q[a] = fminf(fmaxf((c[a] - mn) / ext, 0.0f), 1.0f) * 4095.0f;
+    }
+    const unsigned long long code = (spread3((unsigned)q[0]) << 2) | (spread3((unsigned)q[1]) << 1) | spread3((unsigned)q[2]);
+    keys[k] = (code << IDX_BITS) | (unsigned long long)k;
+}
+
+// Triangles in leaf order.  N = AB x AC is formed in FP64 and rounded once.
+__global__ void emit_leaves(int n, const unsigned long long* __restrict__ keys, const double* __restrict__ raw,
+                            const int* __restrict__ quel_mat, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
+                            float pad, float4* tri, float4* tri_uv, int* tri_orig, float4* leaf_lo, float4* leaf_hi)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const int k = (int)(keys[p] & IDX_MASK);
+    const double* t = raw + 25 * (size_t)k;
+    const double ab[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, ac[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
+    const double nx = ab[1] * ac[2] - ab[2] * ac[1], ny = ab[2] * ac[0] - ab[0] * ac[2], nz = ab[0] * ac[1] - ab[1] * ac[0];
+    tri[3 * p + 0] = make_float4((float)t[0], (float)t[1], (float)t[2], (float)ab[0]);
+    tri[3 * p + 1] = make_float4((float)ab[1], (float)ab[2], (float)ac[0], (float)ac[1]);
+    tri[3 * p + 2] = make_float4((float)ac[2], (float)nx, (float)ny, (float)nz);
+    tri_uv[2 * p + 0] = make_float4((float)t[19], (float)t[20], (float)t[21], (float)t[22]);
+    tri_uv[2 * p + 1] = make_float4((float)t[23], (float)t[24], __int_as_float(quel_mat[k]), __int_as_float(-1));
+    tri_orig[p] = k;
+    const float4 lo = box_lo[k], hi = box_hi[k];
+    leaf_lo[p] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, 0.0f);
+    leaf_hi[p] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, 0.0f);
+}
+
+__device__ __forceinline__ bool same_point(const double* a, const double* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
+
+// A "twin" has the same three vertices and the opposite winding.  In exact arithmetic a ray leaving
+// triangle S from its own surface meets the twin at distance 0 < 1e-7 and the reference rejects it
+// (mesh.h:88); in FP32 that distance is noise, so the twin is skipped by id like S itself.
+__global__ void find_twins(int n, const unsigned long long* __restrict__ keys, const double* __restrict__ raw,
+                           float4* tri_uv, int* n_twins)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned long long code = keys[p] >> IDX_BITS;
+    const double* a = raw + 25 * (size_t)(keys[p] & IDX_MASK);
+    int twin = -1;
+    for (int dir = -1; dir <= 1 && twin < 0; dir += 2) {
+        for (int s = 1; s <= 16; s++) {
+            const int q = p + dir * s;
+            if (q < 0 || q >= n || (keys[q] >> IDX_BITS) != code) break;
+            const double* b = raw + 25 * (size_t)(keys[q] & IDX_MASK);
+            // same vertex set, any rotation of the reversed order
+            const bool rev = (same_point(a, b) && same_point(a + 3, b + 6) && same_point(a + 6, b + 3)) ||
+                             (same_point(a, b + 3) && same_point(a + 3, b) && same_point(a + 6, b + 6)) ||
+                             (same_point(a, b + 6) && same_point(a + 3, b + 3) && same_point(a + 6, b));
+            if (rev) { twin = q; break; }
+        }
+    }
+    if (twin >= 0) {
+        tri_uv[2 * p + 1].w = __int_as_float(twin);
+        atomicAdd(n_twins, 1);
+    }
+}
+
+// ---- Karras 2012 -------------------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const unsigned long long* keys, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    return __clzll((long long)(keys[i] ^ keys[j]));     // keys are unique, so the xor is never 0
+}
+
+// children / parents: internal node c >= 0, leaf p as ~p
+__global__ void build_hierarchy(int n, const unsigned long long* __restrict__ keys, int2* children, int* parent_node, int* parent_leaf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int left = (lo == gamma) ? ~gamma : gamma;
+    const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+    children[i] = make_int2(left, right);
+    if (left < 0) parent_leaf[~left] = i; else parent_node[left] = i;
+    if (right < 0) parent_leaf[~right] = i; else parent_node[right] = i;
+    if (i == 0) parent_node[0] = -1;
+}
+
+__global__ void refit(int n, const int2* __restrict__ children, const int* __restrict__ parent_node, const int* __restrict__ parent_leaf,
+                      const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                      float4* node_lo, float4* node_hi, int* flags, int* max_depth)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int node = parent_leaf[p];
+    int depth = 1;
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(flags + node, 1) == 0) break;          // first arriver stops; the second one has both children ready
+        const int2 ch = children[node];
+        // sibling boxes were written by another thread: read them from L2, not a stale L1 line
+        const float4 alo = ch.x < 0 ? leaf_lo[~ch.x] : __ldcg(node_lo + ch.x);
+        const float4 ahi = ch.x < 0 ? leaf_hi[~ch.x] : __ldcg(node_hi + ch.x);
+        const float4 blo = ch.y < 0 ? leaf_lo[~ch.y] : __ldcg(node_lo + ch.y);
+        const float4 bhi = ch.y < 0 ? leaf_hi[~ch.y] : __ldcg(node_hi + ch.y);
+        node_lo[node] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+        node_hi[node] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+        node = parent_node[node];
+        depth++;
+    }
+    if (node < 0) atomicMax(max_depth, depth);               // this thread reached the root
+}
+
+__device__ __forceinline__ float half_area(float4 lo, float4 hi)
+{
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+__global__ void write_nodes(int n, const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                            const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, float4* nodes, double* sah)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    if (i < n - 1) {
+        const int2 ch = children[i];
+        const float4 alo = ch.x < 0 ? leaf_lo[~ch.x] : node_lo[ch.x], ahi = ch.x < 0 ? leaf_hi[~ch.x] : node_hi[ch.x];
+        const float4 blo = ch.y < 0 ? leaf_lo[~ch.y] : node_lo[ch.y], bhi = ch.y < 0 ? leaf_hi[~ch.y] : node_hi[ch.y];
+        nodes[4 * i + 0] = make_float4(alo.x, ahi.x, alo.y, ahi.y);
+        nodes[4 * i + 1] = make_float4(blo.x, bhi.x, blo.y, bhi.y);
+        nodes[4 * i + 2] = make_float4(alo.z, ahi.z, blo.z, bhi.z);
+        nodes[4 * i + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.0f, 0.0f);
+        // SAH with C_box = 1 per child box test and C_tri = 1 per leaf, relative to the root area
+        const float root_area = fmaxf(half_area(node_lo[0], node_hi[0]), 1e-30f);
+        cost = (double)(half_area(node_lo[i], node_hi[i]) / root_area) * 2.0;
+        if (ch.x < 0) cost += (double)(half_area(alo, ahi) / root_area);
+        if (ch.y < 0) cost += (double)(half_area(blo, bhi) / root_area);
+    }
+    for (int off = 16; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
+    if ((threadIdx.x & 31) == 0 && cost != 0.0) atomicAdd(sah, cost);
+}
+
+struct Scratch {
+    void* ptr = nullptr;
+    ~Scratch() { if (ptr) cudaFree(ptr); }
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+}  // namespace
+
+#define BT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream)
+{
+    out.root = 0; out.max_depth = 0; out.n_twins = 0; out.sah_cost = 0.0; out.tri_tmin = 1e-7f;
+    const int TB = 256;
+
+    if (in.n_spheres > 0) {
+        convert_spheres<<<(in.n_spheres + TB - 1) / TB, TB, 0, stream>>>(in.spheres_raw, in.n_spheres, out.sph, out.sph_mat);
+        BT(cudaGetLastError());
+    }
+    const size_t n_texels = (size_t)in.n_materials * (size_t)in.tex_w * (size_t)in.tex_h;
+    if (n_texels > 0) {
+        int grid = (int)((n_texels + TB - 1) / TB); if (grid > 148 * 16) grid = 148 * 16;
+        convert_texels<<<grid, TB, 0, stream>>>(in.mats_raw, n_texels, in.tex_w * in.tex_h,
+                                                (const MatOverrideDev*)in.overrides_raw, in.n_overrides, out.texels);
+        BT(cudaGetLastError());
+    }
+    const int n = in.n_tris;
+    if (n == 0) return cudaSuccess;
+    if (n > (1 << IDX_BITS)) return cudaErrorInvalidValue;
+
+    // ---- scratch layout ---------------------------------------------------------------------
+    size_t cub_bytes = 0;
+    BT(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, stream));
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
+    const size_t o_box_lo = take(sizeof(float4) * n), o_box_hi = take(sizeof(float4) * n);
+    const size_t o_leaf_lo = take(sizeof(float4) * n), o_leaf_hi = take(sizeof(float4) * n);
+    const size_t o_node_lo = take(sizeof(float4) * n), o_node_hi = take(sizeof(float4) * n);
+    const size_t o_keys_a = take(sizeof(unsigned long long) * n), o_keys_b = take(sizeof(unsigned long long) * n);
+    const size_t o_children = take(sizeof(int2) * n), o_parent_node = take(sizeof(int) * n), o_parent_leaf = take(sizeof(int) * n);
+    const size_t o_flags = take(sizeof(int) * n);
+    const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64)
+    const size_t o_cub = take(cub_bytes);
+    Scratch scratch;
+    BT(cudaMalloc(&scratch.ptr, off));
+    char* base = (char*)scratch.ptr;
+    float4 *box_lo = (float4*)(base + o_box_lo), *box_hi = (float4*)(base + o_box_hi);
+    float4 *leaf_lo = (float4*)(base + o_leaf_lo), *leaf_hi = (float4*)(base + o_leaf_hi);
+    float4 *node_lo = (float4*)(base + o_node_lo), *node_hi = (float4*)(base + o_node_hi);
+    unsigned long long *keys_a = (unsigned long long*)(base + o_keys_a), *keys_b = (unsigned long long*)(base + o_keys_b);
+    int2* children = (int2*)(base + o_children);
+    int *parent_node = (int*)(base + o_parent_node), *parent_leaf = (int*)(base + o_parent_leaf), *flags = (int*)(base + o_flags);
+    int* small = (int*)(base + o_small);
+    double* sah = (double*)(base + o_small + 64);
+
+    // bounds init: min = +big, max = -big in ordered-int space
+    int h_small[64];
+    for (int k = 0; k < 64; k++) h_small[k] = 0;
+    h_small[0] = h_small[1] = h_small[2] = 0x7f7fffff;                 // ord(+FLT_MAX)
+    h_small[3] = h_small[4] = h_small[5] = (int)0x80800000;            // ord(-FLT_MAX) = 0xff7fffff ^ 0x7fffffff
+    BT(cudaMemcpyAsync(small, h_small, sizeof h_small, cudaMemcpyHostToDevice, stream));
+    BT(cudaMemsetAsync(flags, 0, sizeof(int) * n, stream));
+
+    const int grid_n = (n + TB - 1) / TB;
+    tri_bounds<<<grid_n, TB, 0, stream>>>(in.tris_raw, n, box_lo, box_hi, small);
+    morton_keys<<<grid_n, TB, 0, stream>>>(n, box_lo, box_hi, small, keys_a);
+    BT(cudaGetLastError());
+    BT(cub::DeviceRadixSort::SortKeys(base + o_cub, cub_bytes, keys_a, keys_b, n, 0, 64, stream));
+
+    // scene scale -> box padding and the FP32 distance threshold
+    int h_bounds[8];
+    BT(cudaMemcpyAsync(h_bounds, small, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
+    BT(cudaStreamSynchronize(stream));
+    auto ord2f_h = [](int i) { int b = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &b, 4); return f; };
+    const float amax = ord2f_h(h_bounds[6]);
+    const float pad = amax * 4.76837158e-7f + 1e-30f;                    // 2^-21 relative
+    out.tri_tmin = fmaxf(1e-7f, amax * 9.53674316e-7f);                  // 2^-20 relative
+
+    emit_leaves<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, in.quel_mat, box_lo, box_hi, pad,
+                                          out.tri, out.tri_uv, out.tri_orig, leaf_lo, leaf_hi);
+    find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, small + 9);
+    BT(cudaGetLastError());
+    if (n == 1) {
+        out.root = ~0; out.max_depth = 1;
+    } else {
+        build_hierarchy<<<grid_n, TB, 0, stream>>>(n, keys_b, children, parent_node, parent_leaf);
+        refit<<<grid_n, TB, 0, stream>>>(n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, small + 8);
+        write_nodes<<<grid_n, TB, 0, stream>>>(n, children, leaf_lo, leaf_hi, node_lo, node_hi, out.nodes, sah);
+        BT(cudaGetLastError());
+        out.root = 0;
+    }
+    int h_tail[2]; double h_sah = 0.0;
+    BT(cudaMemcpyAsync(h_tail, small + 8, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
+    BT(cudaMemcpyAsync(&h_sah, sah, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    BT(cudaStreamSynchronize(stream));
+    if (n > 1) out.max_depth = h_tail[0];
+    out.n_twins = h_tail[1];
+    out.sah_cost = h_sah;
+    return cudaSuccess;
+}

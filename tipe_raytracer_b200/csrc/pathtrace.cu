@@ -1,0 +1,330 @@
+// pathtrace.cu — K2, the persistent path-tracing kernel, and K4, the resolve (tonemap) kernel.
+//
+// Replaces fill_canva + tracer + closest_hit + ambient_occlusion of the reference
+// (main.c:245-284, 118-242, 52-92, 94-116) for a range of samples of every pixel.
+//
+// Execution model (sm_100a, 148 SMs):
+//   * persistent CTAs, a multiple of the SM count; no per-pixel thread mapping;
+//   * the unit of scheduling is an ITEM = (pixel, chunk of <= S consecutive samples).  Items are
+//     numbered so that 32 consecutive items are the 8x4 pixel tile of one chunk; a warp reserves
+//     32 items at a time from one global counter (one atomic per 32 items) and hands them to its
+//     lanes as they run dry, so lanes never wait for each other's paths ("ray regeneration"):
+//     every trip of the main loop traces exactly one ray per live lane — a bounce ray or an
+//     ambient-occlusion ray — whatever bounce or sample the lane is at;
+//   * a lane keeps the 9 sums of its item in registers as int64 fixed point and flushes them with
+//     9 RED.ADD.64 when the item ends: integer adds commute, so the image is bit-identical for any
+//     schedule, any grid and any split of the samples over GPUs;
+//   * spheres (and their materials) are staged once per CTA into shared memory; BVH nodes,
+//     triangles and texels are read through the read-only path and live in L1/L2.
+#include "trt_isect.cuh"
+#include "trt_kernels.h"
+
+#define PT_THREADS 256
+#define PT_POOL 32
+
+struct PathState {
+    float3 o, d;            // current ray (d is NOT normalised after a mirror/diffuse lerp, main.c:165)
+    float3 d_ao;            // pending ambient-occlusion direction
+    float3 T, L;            // rayColor, incomingLight (main.c:120-121)
+    float3 aov_albedo, aov_normal;
+    float  cur_index;       // the refraction stack collapsed to its top n2 (pile.h)
+    int    bounce;          // i of main.c:132
+    int    alpha_depth;
+    int    src_prim, src_twin;
+    bool   is_alpha;
+};
+
+enum { PH_NEW = 0, PH_BOUNCE = 1, PH_AO = 2, PH_DONE = 3 };
+
+template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+__global__ void __launch_bounds__(PT_THREADS, 2)
+pathtrace_kernel(const __grid_constant__ RenderArgs A)
+{
+    extern __shared__ float4 smem[];
+    float4* s_sph = smem;                                   // [n_spheres]
+    float4* s_mat = smem + A.scene.n_spheres;               // [3*n_spheres]
+    for (int k = threadIdx.x; k < A.scene.n_spheres; k += blockDim.x) s_sph[k] = A.scene.sph[k];
+    for (int k = threadIdx.x; k < 3 * A.scene.n_spheres; k += blockDim.x) s_mat[k] = A.scene.sph_mat[k];
+    __syncthreads();
+
+    const DevScene& sc = A.scene;
+    const int lane = threadIdx.x & 31;
+    const int W = A.W, H = A.H;
+    const size_t npix = (size_t)W * (size_t)H;
+
+    // item bookkeeping (warp-uniform)
+    long long pool_next = 0, pool_end = 0;
+    bool global_dry = false;
+
+    // lane state
+    int phase = PH_NEW;
+    int pixel = -1, px = 0, py = 0, s_cur = 0, s_end = 0;
+    long long acc[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) acc[c] = 0;
+    PathState P;
+    P.o = P.d = P.d_ao = P.T = P.L = P.aov_albedo = P.aov_normal = f3(0, 0, 0);
+    P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.src_prim = TRT_NO_PRIM; P.src_twin = -1; P.is_alpha = false;
+
+    unsigned ray_count = 0;
+    TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
+
+    for (;;) {
+        // ---- 1. lanes without a path: next sample of the item, or next item --------------------
+        if (phase == PH_NEW && s_cur >= s_end) {
+            if (pixel >= 0) {
+#pragma unroll
+                for (int c = 0; c < 9; c++) {
+                    if (acc[c] != 0) atomicAdd((unsigned long long*)(A.accum + (size_t)c * npix + pixel), (unsigned long long)acc[c]);
+                    acc[c] = 0;
+                }
+                pixel = -1;
+            }
+        }
+        {
+            const bool need = (phase == PH_NEW) && (pixel < 0);
+            const unsigned need_mask = __ballot_sync(0xffffffffu, need);
+            if (need_mask != 0) {
+                const int want = __popc(need_mask);
+                const int rank = __popc(need_mask & lanemask_lt());
+                const long long avail = pool_end - pool_next;
+                long long fresh = 0;
+                if (avail < want && !global_dry) {
+                    if (lane == 0) fresh = (long long)atomicAdd(A.item_counter, (unsigned long long)PT_POOL);
+                    fresh = __shfl_sync(0xffffffffu, fresh, 0);
+                }
+                long long item = -1;
+                if (need) {
+                    if (rank < avail) item = pool_next + rank;
+                    else if (!global_dry) item = fresh + (rank - avail);
+                }
+                if (avail < want && !global_dry) {
+                    pool_next = fresh + (want - avail);
+                    pool_end = fresh + PT_POOL;
+                    if (fresh >= A.n_items) global_dry = true;
+                } else {
+                    pool_next += min((long long)want, avail);
+                }
+                if (need) {
+                    if (item >= 0 && item < A.n_items) {
+                        // item -> (tile, chunk, pixel in tile)
+                        const int p = (int)(item & 31);
+                        const long long tc = item >> 5;
+                        const int chunk = (int)(tc % A.n_chunks);
+                        const int tile = (int)(tc / A.n_chunks);
+                        const int tx = tile % A.tiles_x, ty = tile / A.tiles_x;
+                        px = tx * 8 + (p & 7); py = ty * 4 + (p >> 3);
+                        if (px < W && py < H) {
+                            pixel = py * W + px;
+                            s_cur = chunk * A.chunk;
+                            s_end = min(A.spp, s_cur + A.chunk);
+                        }
+                        // else: padding item of an edge tile — stays without work, asks again next trip
+                    } else {
+                        phase = PH_DONE;
+                    }
+                }
+            }
+        }
+        if (__all_sync(0xffffffffu, phase == PH_DONE)) break;
+
+        // ---- 2. start a path: fill_canva's per-sample set-up (main.c:265-271) --------------------
+        if (phase == PH_NEW && pixel >= 0 && s_cur < s_end) {
+            const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 0u, 0u, A.key0, A.key1);
+            const float u = ((float)px + (u01(r.x) - 0.5f)) * A.inv_wm1;
+            const float v = ((float)py + (u01(r.y) - 0.5f)) * A.inv_hm1;
+            const float dx = (u01(r.z) - 0.5f) * A.aperture_x;
+            const float dy = (u01(r.w) - 0.5f) * A.aperture_y;
+            // get_ray (camera.h:42-54); A.cam_corner = coin_bas_gauche - origin, formed in FP64 on the host
+            const float3 direction = fma3(A.cam_hor, u, fma3(A.cam_ver, v, A.cam_corner));
+            const float3 dest = fma3(direction, A.focus, A.cam_origin);
+            P.o = f3(A.cam_origin.x + dx, A.cam_origin.y + dy, A.cam_origin.z);
+            P.d = normalize3(dest - P.o);
+            P.T = f3(1, 1, 1); P.L = f3(0, 0, 0);
+            P.aov_albedo = P.aov_normal = f3(0, 0, 0);
+            P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.is_alpha = false;
+            P.src_prim = TRT_NO_PRIM; P.src_twin = -1;
+            phase = PH_BOUNCE;
+        }
+
+        // ---- 3. one ray per live lane ------------------------------------------------------------
+        const bool live = (phase == PH_BOUNCE) || (phase == PH_AO);
+        HitRec hit; hit.t = 0.0f; hit.prim = TRT_NO_PRIM; hit.u = hit.v = 0.0f;
+        if (live) {
+            const bool ao = (phase == PH_AO);
+            hit = trace_ray<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, ao ? P.d_ao : P.d, P.src_prim, P.src_twin, ao, cnt);
+            ray_count++;
+        }
+
+        bool finished = false;          // path ended this trip
+        float3 out_L = P.L, out_alb = P.aov_albedo, out_nrm = P.aov_normal;
+
+        if (phase == PH_AO) {
+            // ambient_occlusion (main.c:94-116): distance/dst == 1 for a unit direction, so the term
+            // is 1/AO when anything is hit and 0 otherwise.
+            const float occ = (hit.prim != TRT_NO_PRIM) ? A.inv_ao : 0.0f;
+            P.T = P.T * occ;
+            if (P.bounce >= A.bounces) { finished = true; out_L = P.L; out_alb = P.aov_albedo; out_nrm = P.aov_normal; }
+            else phase = PH_BOUNCE;
+        } else if (phase == PH_BOUNCE) {
+            // ---- tracer, one trip of main.c:132-239 ------------------------------------------------
+            const int i = P.bounce;
+            const bool did_hit = hit.prim != TRT_NO_PRIM;
+            Material m;
+            float3 n = f3(0, 0, 0), hp = P.o;
+            int twin = -1;
+            if (did_hit) {
+                hp = fma3(P.d, hit.t, P.o);
+                if (hit.prim < sc.n_spheres) {
+                    const float4 cr = s_sph[hit.prim];
+                    n = normalize3(hp - xyz(cr));                                    // sphere.h:33 (always outward)
+                    m = unpack_material(s_mat[3 * hit.prim], s_mat[3 * hit.prim + 1], s_mat[3 * hit.prim + 2]);
+                } else {
+                    const int leaf = hit.prim - sc.n_spheres;
+                    const float4 r2 = __ldg(sc.tri + 3 * leaf + 2);
+                    n = normalize3(f3(r2.y, r2.z, r2.w));                            // mesh.h:90
+                    m = triangle_material(sc, leaf, hit.u, hit.v, twin);
+                }
+            } else {
+                // the reference reads an uninitialised HitInfo here (main.c:135-139); defined as zeros
+                m = unpack_material(make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0));
+            }
+
+            if (i == 0) { P.aov_albedo = m.diffuse; P.aov_normal = n; }                                   // main.c:137-140
+            if (i == P.alpha_depth && P.is_alpha) {                                                       // main.c:142-150
+                P.aov_albedo = (m.emission_strength > 0.0f) ? m.emission : m.diffuse;
+                P.aov_normal = n;
+                P.is_alpha = false;
+            }
+            out_alb = P.aov_albedo; out_nrm = P.aov_normal;
+
+            if (!did_hit) {
+                finished = true;                                                                          // main.c:236-238
+            } else if (i == P.alpha_depth && m.emission_strength > 0.0f) {
+                // light seen directly (main.c:154-160): HSL round trip with unit gains == identity
+                finished = true; out_L = m.emission; out_alb = m.emission; out_nrm = n;
+            } else {
+                const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 1u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
+                const float3 d_in = P.d;
+                P.o = hp;                                                                                 // main.c:162
+                P.src_prim = hit.prim; P.src_twin = twin;
+                const float3 diffuse_dir = normalize3(n + unit_sphere(u01(r.x), u01(r.y)));               // main.c:163
+                const float3 mirror_dir = reflect3(d_in, n);
+                const float3 mixed = lerp3(diffuse_dir, mirror_dir, m.reflection);                        // main.c:165
+                bool shade = true;
+                if (m.alpha <= 0.99f && m.alpha >= 0.0001f) {                                             // main.c:167-193
+                    float3 nn = n;
+                    float n1 = P.cur_index, n2 = m.index;                  // entering: (top.n2, m), push
+                    const float before = P.cur_index;
+                    P.cur_index = m.index;
+                    if (dot3(d_in, n) > 0.0f) {                            // leaving: pop, swap
+                        nn = -n; n1 = m.index; n2 = before; P.cur_index = before;
+                    }
+                    const float3 refr = refract3(d_in, nn, n1, n2);
+                    const uint4 rc = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 2u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
+                    if (u01(rc.x) > m.alpha) { P.d = refr; shade = false; }
+                    else P.d = mixed;
+                }
+                if (m.alpha > 0.99f) { P.is_alpha = false; P.d = mixed; }                                 // main.c:195-198
+                if (shade && m.alpha < 0.0001f) { P.is_alpha = true; P.alpha_depth++; shade = false; }    // main.c:200-206
+                P.bounce = i + 1;
+                if (shade) {
+                    const float k = A.use_ao ? A.emit_scale_ao : 1.0f;                                    // 1.5 * AO (main.c:210)
+                    P.L = P.L + (m.emission * (m.emission_strength * k)) * P.T;
+                    if (P.T.x > 0.5f || P.T.y > 0.5f || P.T.z > 0.5f) P.T = m.diffuse * (P.T * 1.3f);     // main.c:214-216
+                    P.T = m.diffuse * P.T;
+                    if (A.use_ao) {
+                        P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                         // main.c:100-102
+                        phase = PH_AO;
+                    }
+                }
+                out_L = P.L;
+                if (phase != PH_AO && P.bounce >= A.bounces) finished = true;
+            }
+        }
+
+        if (finished) {
+            acc[0] += to_fixed(out_L.x);   acc[1] += to_fixed(out_L.y);   acc[2] += to_fixed(out_L.z);
+            acc[3] += to_fixed(out_alb.x); acc[4] += to_fixed(out_alb.y); acc[5] += to_fixed(out_alb.z);
+            acc[6] += to_fixed(out_nrm.x); acc[7] += to_fixed(out_nrm.y); acc[8] += to_fixed(out_nrm.z);
+            s_cur++;
+            phase = PH_NEW;
+        }
+    }
+
+    // ---- counters: one atomic per warp ---------------------------------------------------------
+    unsigned long long rc = ray_count;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
+    if (lane == 0 && rc) atomicAdd(A.counters + 0, rc);
+    if (COUNT) {
+        unsigned long long b = cnt.box_tests, t = cnt.tri_tests, s = cnt.sphere_tests;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            b += __shfl_xor_sync(0xffffffffu, b, off);
+            t += __shfl_xor_sync(0xffffffffu, t, off);
+            s += __shfl_xor_sync(0xffffffffu, s, off);
+        }
+        if (lane == 0) { atomicAdd(A.counters + 1, b); atomicAdd(A.counters + 2, t); atomicAdd(A.counters + 3, s); }
+    }
+}
+
+// ---- K4: resolve — write_color_canva (rtutility.h:56-71) + the AOV means (main.c:275-279) -------
+// Sums up to n_src accumulation buffers (this GPU's and, over NVLink peer mappings, the other
+// GPUs' of the ctx) while tonemapping, so a multi-GPU render needs no separate reduction pass.
+__global__ void __launch_bounds__(256)
+resolve_kernel(ResolveArgs R)
+{
+    const size_t npix = (size_t)R.W * (size_t)R.H;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+        long long s[9];
+#pragma unroll
+        for (int c = 0; c < 9; c++) s[c] = 0;
+        for (int k = 0; k < R.n_src; k++) {
+            const long long* src = R.src[k];
+#pragma unroll
+            for (int c = 0; c < 9; c++) s[c] += src[(size_t)c * npix + p];
+        }
+        const double rapport = 1.0 / (double)R.divisor;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double sum = (double)s[c] * TRT_ACCUM_INV_SCALE;
+            float r = sqrtf((float)(rapport * sum));                 // sqrtf: FLOAT square root, like the reference
+            double cl = (double)r;
+            cl = cl < 0.0 ? 0.0 : (cl > 0.999 ? 0.999 : cl);         // NaN falls through both tests, as in clamp()
+            R.canva[3 * p + c] = (double)(int)(256.0 * cl);
+            R.albedo[3 * p + c] = ((double)s[3 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
+            R.normal[3 * p + c] = ((double)s[6 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
+        }
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
+{
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT><<<grid, PT_THREADS, smem, stream>>>(A);
+    return cudaGetLastError();
+}
+
+cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, bool brute, bool count_tests, cudaStream_t stream)
+{
+    const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4);
+    const int grid = n_sms * 2;
+    const bool has_tris = A.scene.n_tris > 0;
+    if (!has_tris) return count_tests ? launch_variant<false, false, true>(A, grid, smem, stream)
+                                      : launch_variant<false, false, false>(A, grid, smem, stream);
+    if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
+                                  : launch_variant<true, true, false>(A, grid, smem, stream);
+    return count_tests ? launch_variant<true, false, true>(A, grid, smem, stream)
+                       : launch_variant<true, false, false>(A, grid, smem, stream);
+}
+
+cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream)
+{
+    const size_t npix = (size_t)R.W * (size_t)R.H;
+    int grid = (int)((npix + 255) / 256);
+    if (grid > n_sms * 8) grid = n_sms * 8;
+    resolve_kernel<<<grid, 256, 0, stream>>>(R);
+    return cudaGetLastError();
+}

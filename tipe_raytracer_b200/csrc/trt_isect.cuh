@@ -1,0 +1,230 @@
+// trt_isect.cuh — FP32 intersection routines of the path-tracing kernel.
+//
+// Semantics follow the reference's CPU path (cited per function); the arithmetic is re-derived
+// for FP32 on the GPU:
+//   * rays restart exactly on the surface they left (main.c:162).  In FP64 the reference gets away
+//     with absolute thresholds (1e-4 spheres, 1e-7 triangles); in FP32 the primitive the ray
+//     starts on is identified by id instead: a source sphere is solved with c = 0 exactly, a source
+//     triangle (and its coincident opposite-facing twin in double-faced meshes) is skipped —
+//     both are what the reference's thresholds amount to in exact arithmetic;
+//   * the quadratic uses the cancellation-free root pair (q/a, c/q);
+//   * un-normalised directions are legal (main.c:165 lerps without renormalising): distances are
+//     in units of |d| everywhere, exactly like the reference.
+#pragma once
+
+#include "trt_device.cuh"
+
+#define TRT_NO_PRIM (-1)
+#define TRT_STACK_DEPTH 64
+
+struct Ray {
+    float3 o, d;
+};
+
+struct HitRec {
+    float t;        // in units of |d|; +inf when nothing was hit
+    int   prim;     // TRT_NO_PRIM, sphere k -> k, triangle at leaf position p -> n_spheres + p
+    float u, v;     // Moller-Trumbore barycentrics of the winning triangle (weights of B and C)
+};
+
+struct TraceCounters {
+    unsigned box_tests, tri_tests, sphere_tests;
+};
+
+// sphere.h:13-47.  Returns the accepted root (near if >= 1e-4, else far if >= 1e-4) or -1.
+// `on_surface`: the ray starts on this very sphere => c = |oc|^2 - r^2 is 0 by construction.
+__device__ __forceinline__ float sphere_root(float4 cr, float3 o, float3 d, float a, bool on_surface)
+{
+    const float3 oc = f3(o.x - cr.x, o.y - cr.y, o.z - cr.z);
+    const float hb = dot3(oc, d);                                   // b / 2
+    float c = fmaf(oc.x, oc.x, fmaf(oc.y, oc.y, fmaf(oc.z, oc.z, -cr.w * cr.w)));
+    if (on_surface) c = 0.0f;
+    const float qd = fmaf(hb, hb, -a * c);                          // discriminant / 4
+    if (!(qd > 0.0f)) return -1.0f;                                 // sphere.h:27 (strict)
+    const float sq = sqrtf(qd);
+    const float q = -(hb + copysignf(sq, hb));                      // never cancels
+    const float ra = __fdividef(q, a);
+    const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
+    const float t1 = fminf(ra, rb), t2 = fmaxf(ra, rb);
+    if (t1 >= 1e-4f) return t1;                                     // sphere.h:29
+    if (t2 >= 1e-4f) return t2;                                     // sphere.h:38
+    return -1.0f;
+}
+
+// mesh.h:70-94, with A, AB, AC, N = ABxAC precomputed.  Front faces only (det >= 1e-6),
+// dst >= tmin (FP32 stand-in for 1e-7), u, v, w >= 1e-7.
+__device__ __forceinline__ bool triangle_test(float4 r0, float4 r1, float4 r2, float3 o, float3 d, float tmin,
+                                              float& t, float& u, float& v)
+{
+    const float3 A = f3(r0.x, r0.y, r0.z), AB = f3(r0.w, r1.x, r1.y), AC = f3(r1.z, r1.w, r2.x), N = f3(r2.y, r2.z, r2.w);
+    const float det = -dot3(d, N);
+    const float3 ao = o - A;
+    const float3 dao = cross3(ao, d);
+    const float inv = __frcp_rn(det);
+    t = dot3(ao, N) * inv;
+    u = dot3(AC, dao) * inv;
+    v = -dot3(AB, dao) * inv;
+    const float w = 1.0f - u - v;
+    return det >= 1e-6f && t >= tmin && u >= 1e-7f && v >= 1e-7f && w >= 1e-7f;
+}
+
+// closest_hit (main.c:52-92): spheres in order, then triangles; strict '<' keeps the first
+// primitive on exact ties (for triangles: the lower index in the caller's array).
+// any_hit: the caller only needs "hit anything" (ambient_occlusion, main.c:104-106).
+template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+__device__ __forceinline__ HitRec trace_ray(const DevScene& sc, const float4* __restrict__ s_sph,
+                                            float3 o, float3 d, int src_prim, int src_twin, bool any_hit,
+                                            TraceCounters& cnt)
+{
+    HitRec best;
+    best.t = __int_as_float(0x7f800000);
+    best.prim = TRT_NO_PRIM;
+    best.u = best.v = 0.0f;
+
+    const float a = dot3(d, d);
+    const int ns = sc.n_spheres;
+    for (int k = 0; k < ns; k++) {
+        const float t = sphere_root(s_sph[k], o, d, a, k == src_prim);
+        if (t >= 0.0f && t < best.t) { best.t = t; best.prim = k; }
+    }
+    if (COUNT) cnt.sphere_tests += ns;
+
+    if (!HAS_TRIS || sc.n_tris == 0) return best;
+    if (any_hit && best.prim != TRT_NO_PRIM) return best;
+
+    const int src_leaf = src_prim - ns, twin_leaf = src_twin;      // leaf positions to skip (negative: none)
+    const float tmin = sc.tri_tmin;
+
+    if (BRUTE) {
+        // linear scan in the caller's order, like main.c:81-90
+        for (int p = 0; p < sc.n_tris; p++) {
+            if (p == src_leaf || p == twin_leaf) continue;
+            float t, u, v;
+            const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+            if (COUNT) cnt.tri_tests++;
+            if (triangle_test(r0, r1, r2, o, d, tmin, t, u, v)) {
+                bool take = t < best.t;
+                if (t == best.t && best.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (best.prim - ns));
+                if (take) { best.t = t; best.prim = ns + p; best.u = u; best.v = v; }
+            }
+        }
+        return best;
+    }
+
+    // ---- BVH2 traversal, stack in local memory --------------------------------------------
+    const float ooeps = 1e-30f;
+    const float3 idir = f3(1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x)),
+                           1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y)),
+                           1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z)));
+    const float3 ood = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+
+    int stack[TRT_STACK_DEPTH];
+    int sp = 0;
+    int node = sc.root;
+    const int SENTINEL = 0x7fffffff;
+    stack[sp++] = SENTINEL;
+
+    while (node != SENTINEL) {
+        while (node >= 0 && node != SENTINEL) {
+            const float4 n0 = __ldg(sc.nodes + 4 * node), n1 = __ldg(sc.nodes + 4 * node + 1);
+            const float4 n2 = __ldg(sc.nodes + 4 * node + 2);
+            const int4 ch = __ldg((const int4*)(sc.nodes + 4 * node + 3));
+            if (COUNT) cnt.box_tests += 2;
+            // child 0: x in (n0.x, n0.y), y in (n0.z, n0.w), z in (n2.x, n2.y)
+            const float c0lox = fmaf(n0.x, idir.x, -ood.x), c0hix = fmaf(n0.y, idir.x, -ood.x);
+            const float c0loy = fmaf(n0.z, idir.y, -ood.y), c0hiy = fmaf(n0.w, idir.y, -ood.y);
+            const float c0loz = fmaf(n2.x, idir.z, -ood.z), c0hiz = fmaf(n2.y, idir.z, -ood.z);
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
+            // child 1: x in (n1.x, n1.y), y in (n1.z, n1.w), z in (n2.z, n2.w)
+            const float c1lox = fmaf(n1.x, idir.x, -ood.x), c1hix = fmaf(n1.y, idir.x, -ood.x);
+            const float c1loy = fmaf(n1.z, idir.y, -ood.y), c1hiy = fmaf(n1.w, idir.y, -ood.y);
+            const float c1loz = fmaf(n2.z, idir.z, -ood.z), c1hiz = fmaf(n2.w, idir.z, -ood.z);
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
+            const bool h0 = c0max >= c0min, h1 = c1max >= c1min;
+            if (!h0 && !h1) { node = stack[--sp]; }
+            else {
+                node = h0 ? ch.x : ch.y;
+                if (h0 && h1) {
+                    int far = ch.y;
+                    if (c1min < c0min) { far = ch.x; node = ch.y; }
+                    if (sp < TRT_STACK_DEPTH) stack[sp++] = far;
+                }
+            }
+        }
+        if (node == SENTINEL) break;
+        // leaf: one triangle at leaf position ~node
+        const int p = ~node;
+        if (p != src_leaf && p != twin_leaf) {
+            float t, u, v;
+            const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+            if (COUNT) cnt.tri_tests++;
+            if (triangle_test(r0, r1, r2, o, d, tmin, t, u, v)) {
+                bool take = t < best.t;
+                if (t == best.t && best.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (best.prim - ns));
+                if (take) {
+                    best.t = t; best.prim = ns + p; best.u = u; best.v = v;
+                    if (any_hit) break;
+                }
+            }
+        }
+        node = stack[--sp];
+    }
+    return best;
+}
+
+// ---- material at the hit ----------------------------------------------------------------------
+struct Material {
+    float3 diffuse; float alpha;
+    float3 emission; float emission_strength;
+    float reflection, index;
+};
+
+__device__ __forceinline__ Material unpack_material(float4 m0, float4 m1, float4 m2)
+{
+    Material m;
+    m.diffuse = xyz(m0); m.alpha = m0.w;
+    m.emission = xyz(m1); m.emission_strength = m1.w;
+    m.reflection = m2.x; m.index = m2.y;
+    return m;
+}
+
+// tri_uvmapping (texture.h:44-90): uv from the barycentrics (weights w,u,v for A,B,C — equal to the
+// reference's signed-area barycentrics), tiling by fmod, nearest texel, slab by
+// material ordinal.  Per-ordinal overrides are already baked into the texel table.
+__device__ __forceinline__ Material triangle_material(const DevScene& sc, int leaf_pos, float u, float v, int& twin_out)
+{
+    const float4 q0 = __ldg(sc.tri_uv + 2 * leaf_pos), q1 = __ldg(sc.tri_uv + 2 * leaf_pos + 1);
+    const float w = 1.0f - u - v;
+    float tu = fmaf(w, q0.x, fmaf(u, q0.z, v * q1.x));
+    float tv = fmaf(w, q0.y, fmaf(u, q0.w, v * q1.y));
+    tu -= truncf(tu); tv -= truncf(tv);                 // fmod(x, 1.0)
+    if (tu < 0.0f) tu += 1.0f;
+    if (tv < 0.0f) tv += 1.0f;
+    const int x = min((int)(tu * (float)sc.tex_w), sc.tex_w - 1);
+    const int y = min((int)(tv * (float)sc.tex_h), sc.tex_h - 1);
+    const int ordinal = __float_as_int(q1.z);
+    twin_out = __float_as_int(q1.w);
+    const size_t texel = (size_t)(y * sc.tex_w + x) + (size_t)sc.tex_h * (size_t)sc.tex_w * (size_t)ordinal;
+    const float4* rec = sc.texels + 3 * texel;
+    return unpack_material(__ldg(rec), __ldg(rec + 1), __ldg(rec + 2));
+}
+
+// reflected_vec (rtutility.h:205-208)
+__device__ __forceinline__ float3 reflect3(float3 v, float3 n) { return fma3(n, -2.0f * dot3(v, n), v); }
+
+// refracted_vec (rtutility.h:210-227): both indices squared first, result not renormalised,
+// total internal reflection -> mirror.
+__device__ __forceinline__ float3 refract3(float3 v, float3 n, float n1, float n2)
+{
+    n1 *= n1; n2 *= n2;
+    const float rho = n1 / n2;
+    const float vn = dot3(n, v);
+    const float radical = 1.0f - (rho * rho) * (1.0f - vn * vn);
+    if (radical > 0.0f) {
+        const float3 tang = (v - n * vn) * rho;
+        return tang - n * sqrtf(radical);
+    }
+    return reflect3(v, n);
+}

@@ -1,0 +1,81 @@
+// trt_kernels.h — host-visible launch interface of the CUDA translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "trt_device.cuh"
+
+#define TRT_MAX_RESOLVE_SOURCES 16
+
+// Arguments of the path-tracing kernel (passed as one __grid_constant__ struct).
+struct RenderArgs {
+    DevScene scene;
+    int W, H;
+    int spp;                // samples rendered by this launch (of every pixel)
+    int sample_offset;      // global index of the first of them (Philox counter)
+    int bounces;            // nbRebondMax
+    int use_ao;
+    float inv_ao;           // 1 / AO_intensity
+    float emit_scale_ao;    // 1.5 * AO_intensity
+    float focus, aperture_x, aperture_y;
+    float inv_wm1, inv_hm1; // 1/(W-1), 1/(H-1)
+    float3 cam_origin, cam_hor, cam_ver, cam_corner;   // cam_corner = coin_bas_gauche - origin (FP64 on host)
+    uint32_t key0, key1;
+    // work decomposition
+    int chunk, n_chunks, tiles_x, tiles_y;
+    long long n_items;
+    unsigned long long* item_counter;   // zeroed before launch
+    unsigned long long* counters;       // [0] rays [1] box tests [2] triangle tests [3] sphere tests
+    long long* accum;                   // planar [9][W*H] int64, value * 2^28
+};
+
+struct ResolveArgs {
+    int W, H, divisor, n_src;
+    const long long* src[TRT_MAX_RESOLVE_SOURCES];
+    double *canva, *albedo, *normal;    // [W*H][3]
+};
+
+cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, bool brute, bool count_tests, cudaStream_t stream);
+cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
+
+// K1: FP64 primary visibility, linear scan in the caller's order.
+struct PrimaryArgs {
+    DevScene scene;
+    int W, H;
+    double focus;
+    double cam[12];                     // origin, horizontal, vertical, coin_bas_gauche
+    double* t; int* id; double* normal; double* albedo;    // any may be null
+};
+cudaError_t trt_launch_primary(const PrimaryArgs& P, cudaStream_t stream);
+
+// Scene conversion + BVH build (K3).  Raw = the caller's FP64 AoS arrays, already on the device.
+struct BuildInputs {
+    const double* spheres_raw;   int n_spheres;     // 14 doubles each
+    const double* tris_raw;      int n_tris;        // 25 doubles each
+    const double* mats_raw;      int tex_w, tex_h, n_materials;   // 10 doubles per texel
+    const int*    quel_mat;                         // [n_tris]
+    const double* overrides_raw; int n_overrides;   // trt_mat_override, 8 doubles each (first = ordinal|mask)
+};
+struct BuildOutputs {            // device buffers allocated by the caller with these element counts
+    float4* sph;        // n_spheres
+    float4* sph_mat;    // 3*n_spheres
+    float4* tri;        // 3*n_tris
+    float4* tri_uv;     // 2*n_tris
+    int*    tri_orig;   // n_tris
+    float4* nodes;      // 4*max(n_tris-1,1)
+    float4* texels;     // 3*n_materials*tex_w*tex_h
+    // filled by the build
+    int root;
+    float tri_tmin;
+    int max_depth, n_twins;
+    double sah_cost;
+};
+cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream);
+
+// Known-answer kernels (leaf functions of K2 run over arrays).
+cudaError_t trt_kat_launch_sphere(int n, const float4* cr, const float* ray, int* hit, float* dst, float* point, float* normal, cudaStream_t s);
+cudaError_t trt_kat_launch_triangle(int n, const float* abc, const float* ray, int* hit, float* dst_u_v, cudaStream_t s);
+cudaError_t trt_kat_launch_refract(int n, const float* in8, float* out3, cudaStream_t s);
+cudaError_t trt_kat_launch_philox(int n, const uint32_t* ctr_key, uint32_t* out4, cudaStream_t s);
+cudaError_t trt_kat_launch_tonemap(int n, const long long* sums, int spp, double* out, cudaStream_t s);
