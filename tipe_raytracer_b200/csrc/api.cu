@@ -6,6 +6,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -125,7 +126,14 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.cam_corner = make_float3((float)(c.coin_bas_gauche.e[0] - c.origin.e[0]), (float)(c.coin_bas_gauche.e[1] - c.origin.e[1]),
                                (float)(c.coin_bas_gauche.e[2] - c.origin.e[2]));
     A.key0 = (uint32_t)(p->seed & 0xffffffffu); A.key1 = (uint32_t)(p->seed >> 32);
-    A.chunk = spp < 32 ? spp : 32;
+    // tuning knobs (defaults chosen from measurements on B200); env overrides are for experiments
+    auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
+    const int chunk_max = knob("TRT_TUNE_CHUNK", 32);
+    A.min_steps = knob("TRT_TUNE_MIN_STEPS", 8);
+    A.exit_num = knob("TRT_TUNE_EXIT", 20);
+    A.vote = knob("TRT_TUNE_VOTE", 0);
+    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 2);
+    A.chunk = spp < chunk_max ? spp : chunk_max;
     A.n_chunks = (spp + A.chunk - 1) / A.chunk;
     A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;
     A.n_items = (long long)A.tiles_x * A.tiles_y * A.n_chunks * 32;
@@ -134,7 +142,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.accum = accum;
     CU(ctx, cudaMemsetAsync(d.ctrs, 0, sizeof(unsigned long long) * 8, d.stream));
     CU(ctx, cudaEventRecord(d.ev_a, d.stream));
-    CU(ctx, trt_launch_pathtrace(A, d.n_sms, (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, (p->flags & TRT_FLAG_COUNT_TESTS) != 0, d.stream));
+    CU(ctx, trt_launch_pathtrace(A, d.n_sms, blocks_per_sm, (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, (p->flags & TRT_FLAG_COUNT_TESTS) != 0, d.stream));
     CU(ctx, cudaEventRecord(d.ev_b, d.stream));
     CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, d.stream));
     return TRT_OK;

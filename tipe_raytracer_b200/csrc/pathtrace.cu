@@ -21,6 +21,9 @@
 
 #define PT_THREADS 256
 #define PT_POOL 32
+// Traversal-loop exit policy (RenderArgs.min_steps / exit_num): a warp always takes min_steps BVH steps,
+// then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
+// so that the lanes that are done get shaded and re-armed instead of idling.
 
 struct PathState {
     float3 o, d;            // current ray (d is NOT normalised after a mirror/diffuse lerp, main.c:165)
@@ -36,21 +39,25 @@ struct PathState {
 
 enum { PH_NEW = 0, PH_BOUNCE = 1, PH_AO = 2, PH_DONE = 3 };
 
-template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE>
 __global__ void __launch_bounds__(PT_THREADS, 2)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
     extern __shared__ float4 smem[];
     float4* s_sph = smem;                                   // [n_spheres]
     float4* s_mat = smem + A.scene.n_spheres;               // [3*n_spheres]
+    long long* s_acc = (long long*)(smem + 4 * A.scene.n_spheres);   // [9][PT_THREADS] per-lane sums of the current item
     for (int k = threadIdx.x; k < A.scene.n_spheres; k += blockDim.x) s_sph[k] = A.scene.sph[k];
     for (int k = threadIdx.x; k < 3 * A.scene.n_spheres; k += blockDim.x) s_mat[k] = A.scene.sph_mat[k];
+#pragma unroll
+    for (int c = 0; c < 9; c++) s_acc[c * PT_THREADS + threadIdx.x] = 0;
     __syncthreads();
 
     const DevScene& sc = A.scene;
     const int lane = threadIdx.x & 31;
     const int W = A.W, H = A.H;
     const size_t npix = (size_t)W * (size_t)H;
+    long long* my_acc = s_acc + threadIdx.x;
 
     // item bookkeeping (warp-uniform)
     long long pool_next = 0, pool_end = 0;
@@ -59,27 +66,124 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     // lane state
     int phase = PH_NEW;
     int pixel = -1, px = 0, py = 0, s_cur = 0, s_end = 0;
-    long long acc[9];
-#pragma unroll
-    for (int c = 0; c < 9; c++) acc[c] = 0;
     PathState P;
     P.o = P.d = P.d_ao = P.T = P.L = P.aov_albedo = P.aov_normal = f3(0, 0, 0);
     P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.src_prim = TRT_NO_PRIM; P.src_twin = -1; P.is_alpha = false;
+    Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
+    int stack[TRT_STACK_DEPTH];
 
     unsigned ray_count = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
 
     for (;;) {
-        // ---- 1. lanes without a path: next sample of the item, or next item --------------------
-        if (phase == PH_NEW && s_cur >= s_end) {
-            if (pixel >= 0) {
-#pragma unroll
-                for (int c = 0; c < 9; c++) {
-                    if (acc[c] != 0) atomicAdd((unsigned long long*)(A.accum + (size_t)c * npix + pixel), (unsigned long long)acc[c]);
-                    acc[c] = 0;
+        bool new_ray = false;
+
+        // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
+        if (tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)) {
+            bool finished = false;          // path ended
+            float3 out_L = P.L, out_alb = P.aov_albedo, out_nrm = P.aov_normal;
+            const bool did_hit = tr.prim != TRT_NO_PRIM;
+
+            if (phase == PH_AO) {
+                // ambient_occlusion (main.c:94-116): distance/dst == 1 for a unit direction, so the term
+                // is 1/AO when anything is hit and 0 otherwise.
+                P.T = P.T * (did_hit ? A.inv_ao : 0.0f);
+                if (P.bounce >= A.bounces) finished = true;
+                else { phase = PH_BOUNCE; new_ray = true; }
+            } else {
+                const int i = P.bounce;
+                Material m;
+                float3 n = f3(0, 0, 0), hp = P.o;
+                int twin = -1;
+                if (did_hit) {
+                    hp = fma3(P.d, tr.t, P.o);
+                    if (tr.prim < sc.n_spheres) {
+                        const float4 cr = s_sph[tr.prim];
+                        n = normalize3(hp - xyz(cr));                                    // sphere.h:33 (always outward)
+                        m = unpack_material(s_mat[3 * tr.prim], s_mat[3 * tr.prim + 1], s_mat[3 * tr.prim + 2]);
+                    } else {
+                        const int leaf = tr.prim - sc.n_spheres;
+                        const float4 r2 = __ldg(sc.tri + 3 * leaf + 2);
+                        n = normalize3(f3(r2.y, r2.z, r2.w));                            // mesh.h:90
+                        m = triangle_material(sc, leaf, tr.u, tr.v, twin);
+                    }
+                } else {
+                    // the reference reads an uninitialised HitInfo here (main.c:135-139); defined as zeros
+                    m = unpack_material(make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0));
                 }
-                pixel = -1;
+
+                if (i == 0) { P.aov_albedo = m.diffuse; P.aov_normal = n; }                                   // main.c:137-140
+                if (i == P.alpha_depth && P.is_alpha) {                                                       // main.c:142-150
+                    P.aov_albedo = (m.emission_strength > 0.0f) ? m.emission : m.diffuse;
+                    P.aov_normal = n;
+                    P.is_alpha = false;
+                }
+                out_alb = P.aov_albedo; out_nrm = P.aov_normal;
+
+                if (!did_hit) {
+                    finished = true;                                                                          // main.c:236-238
+                } else if (i == P.alpha_depth && m.emission_strength > 0.0f) {
+                    // light seen directly (main.c:154-160): HSL round trip with unit gains == identity
+                    finished = true; out_L = m.emission; out_alb = m.emission; out_nrm = n;
+                } else {
+                    const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 1u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
+                    const float3 d_in = P.d;
+                    P.o = hp;                                                                                 // main.c:162
+                    P.src_prim = tr.prim; P.src_twin = twin;
+                    const float3 diffuse_dir = normalize3(n + unit_sphere(u01(r.x), u01(r.y)));               // main.c:163
+                    const float3 mirror_dir = reflect3(d_in, n);
+                    const float3 mixed = lerp3(diffuse_dir, mirror_dir, m.reflection);                        // main.c:165
+                    bool shade = true;
+                    if (m.alpha <= 0.99f && m.alpha >= 0.0001f) {                                             // main.c:167-193
+                        float3 nn = n;
+                        float n1 = P.cur_index, n2 = m.index;                  // entering: (top.n2, m), push
+                        const float before = P.cur_index;
+                        P.cur_index = m.index;
+                        if (dot3(d_in, n) > 0.0f) {                            // leaving: pop, swap
+                            nn = -n; n1 = m.index; n2 = before; P.cur_index = before;
+                        }
+                        const float3 refr = refract3(d_in, nn, n1, n2);
+                        const uint4 rc = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 2u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
+                        if (u01(rc.x) > m.alpha) { P.d = refr; shade = false; }
+                        else P.d = mixed;
+                    }
+                    if (m.alpha > 0.99f) { P.is_alpha = false; P.d = mixed; }                                 // main.c:195-198
+                    if (shade && m.alpha < 0.0001f) { P.is_alpha = true; P.alpha_depth++; shade = false; }    // main.c:200-206
+                    P.bounce = i + 1;
+                    if (shade) {
+                        const float k = A.use_ao ? A.emit_scale_ao : 1.0f;                                    // 1.5 * AO (main.c:210)
+                        P.L = P.L + (m.emission * (m.emission_strength * k)) * P.T;
+                        if (P.T.x > 0.5f || P.T.y > 0.5f || P.T.z > 0.5f) P.T = m.diffuse * (P.T * 1.3f);     // main.c:214-216
+                        P.T = m.diffuse * P.T;
+                        if (A.use_ao) {
+                            P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                         // main.c:100-102
+                            phase = PH_AO;
+                        }
+                    }
+                    out_L = P.L;
+                    if (phase != PH_AO && P.bounce >= A.bounces) finished = true;
+                    else new_ray = true;
+                }
             }
+            if (finished) {
+                my_acc[0 * PT_THREADS] += to_fixed(out_L.x);   my_acc[1 * PT_THREADS] += to_fixed(out_L.y);   my_acc[2 * PT_THREADS] += to_fixed(out_L.z);
+                my_acc[3 * PT_THREADS] += to_fixed(out_alb.x); my_acc[4 * PT_THREADS] += to_fixed(out_alb.y); my_acc[5 * PT_THREADS] += to_fixed(out_alb.z);
+                my_acc[6 * PT_THREADS] += to_fixed(out_nrm.x); my_acc[7 * PT_THREADS] += to_fixed(out_nrm.y); my_acc[8 * PT_THREADS] += to_fixed(out_nrm.z);
+                s_cur++;
+                phase = PH_NEW;
+                new_ray = false;
+            }
+        }
+
+        // ---- A2. lanes without a path: flush a finished item, take the next sample or the next item ---
+        if (phase == PH_NEW && s_cur >= s_end && pixel >= 0) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) {
+                const long long v = my_acc[c * PT_THREADS];
+                if (v != 0) atomicAdd((unsigned long long*)(A.accum + (size_t)c * npix + pixel), (unsigned long long)v);
+                my_acc[c * PT_THREADS] = 0;
+            }
+            pixel = -1;
         }
         {
             const bool need = (phase == PH_NEW) && (pixel < 0);
@@ -126,9 +230,11 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
             }
         }
-        if (__all_sync(0xffffffffu, phase == PH_DONE)) break;
+        const unsigned live_mask = __ballot_sync(0xffffffffu, phase != PH_DONE);
+        if (live_mask == 0) break;
 
-        // ---- 2. start a path: fill_canva's per-sample set-up (main.c:265-271) --------------------
+        // ---- A3. start a path: fill_canva's per-sample set-up (main.c:265-271) --------------------
+        if (phase == PH_NEW && pixel >= 0 && s_cur < s_end && A.bounces <= 0) s_cur = s_end;   // main.c:132 never iterates: all sums stay 0
         if (phase == PH_NEW && pixel >= 0 && s_cur < s_end) {
             const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 0u, 0u, A.key0, A.key1);
             const float u = ((float)px + (u01(r.x) - 0.5f)) * A.inv_wm1;
@@ -145,110 +251,40 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.is_alpha = false;
             P.src_prim = TRT_NO_PRIM; P.src_twin = -1;
             phase = PH_BOUNCE;
+            new_ray = true;
         }
 
-        // ---- 3. one ray per live lane ------------------------------------------------------------
-        const bool live = (phase == PH_BOUNCE) || (phase == PH_AO);
-        HitRec hit; hit.t = 0.0f; hit.prim = TRT_NO_PRIM; hit.u = hit.v = 0.0f;
-        if (live) {
-            const bool ao = (phase == PH_AO);
-            hit = trace_ray<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, ao ? P.d_ao : P.d, P.src_prim, P.src_twin, ao, cnt);
+        // ---- A4. new rays: sphere scan + traversal set-up -------------------------------------------
+        const bool ao = (phase == PH_AO);
+        const float3 rd = ao ? P.d_ao : P.d;
+        if (new_ray) {
+            ray_begin<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, rd, P.src_prim, P.src_twin, ao, tr, stack, cnt);
             ray_count++;
         }
 
-        bool finished = false;          // path ended this trip
-        float3 out_L = P.L, out_alb = P.aov_albedo, out_nrm = P.aov_normal;
-
-        if (phase == PH_AO) {
-            // ambient_occlusion (main.c:94-116): distance/dst == 1 for a unit direction, so the term
-            // is 1/AO when anything is hit and 0 otherwise.
-            const float occ = (hit.prim != TRT_NO_PRIM) ? A.inv_ao : 0.0f;
-            P.T = P.T * occ;
-            if (P.bounce >= A.bounces) { finished = true; out_L = P.L; out_alb = P.aov_albedo; out_nrm = P.aov_normal; }
-            else phase = PH_BOUNCE;
-        } else if (phase == PH_BOUNCE) {
-            // ---- tracer, one trip of main.c:132-239 ------------------------------------------------
-            const int i = P.bounce;
-            const bool did_hit = hit.prim != TRT_NO_PRIM;
-            Material m;
-            float3 n = f3(0, 0, 0), hp = P.o;
-            int twin = -1;
-            if (did_hit) {
-                hp = fma3(P.d, hit.t, P.o);
-                if (hit.prim < sc.n_spheres) {
-                    const float4 cr = s_sph[hit.prim];
-                    n = normalize3(hp - xyz(cr));                                    // sphere.h:33 (always outward)
-                    m = unpack_material(s_mat[3 * hit.prim], s_mat[3 * hit.prim + 1], s_mat[3 * hit.prim + 2]);
+        // ---- B. BVH traversal, left early when too few lanes are still inside ------------------------
+        if (HAS_TRIS && !BRUTE) {
+            const float3 idir = safe_inverse(rd);
+            const float3 ood = f3(P.o.x * idir.x, P.o.y * idir.y, P.o.z * idir.z);
+            const int src_leaf = P.src_prim - sc.n_spheres, twin_leaf = P.src_twin;
+            const int exit_below = (A.exit_num * __popc(live_mask) + 31) >> 5;
+            for (int step = 0;; step++) {
+                const bool inside = tr.node != TRT_TRAV_DONE;
+                const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
+                if (in_mask == 0) break;
+                if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
+                if (MODE == 0) {
+                    // if-if: every trip, each lane does whatever it is at (a node visit or a leaf test)
+                    if (inside) {
+                        if (tr.node >= 0) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
+                        else bvh_leaf<COUNT>(sc, P.o, rd, src_leaf, twin_leaf, ao, tr, stack, cnt);
+                    }
                 } else {
-                    const int leaf = hit.prim - sc.n_spheres;
-                    const float4 r2 = __ldg(sc.tri + 3 * leaf + 2);
-                    n = normalize3(f3(r2.y, r2.z, r2.w));                            // mesh.h:90
-                    m = triangle_material(sc, leaf, hit.u, hit.v, twin);
+                    // while-while: descend until this lane holds a leaf (or is done), then all leaves together
+                    while (tr.node >= 0 && tr.node != TRT_TRAV_DONE) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
+                    if (tr.node < 0) bvh_leaf<COUNT>(sc, P.o, rd, src_leaf, twin_leaf, ao, tr, stack, cnt);
                 }
-            } else {
-                // the reference reads an uninitialised HitInfo here (main.c:135-139); defined as zeros
-                m = unpack_material(make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0));
             }
-
-            if (i == 0) { P.aov_albedo = m.diffuse; P.aov_normal = n; }                                   // main.c:137-140
-            if (i == P.alpha_depth && P.is_alpha) {                                                       // main.c:142-150
-                P.aov_albedo = (m.emission_strength > 0.0f) ? m.emission : m.diffuse;
-                P.aov_normal = n;
-                P.is_alpha = false;
-            }
-            out_alb = P.aov_albedo; out_nrm = P.aov_normal;
-
-            if (!did_hit) {
-                finished = true;                                                                          // main.c:236-238
-            } else if (i == P.alpha_depth && m.emission_strength > 0.0f) {
-                // light seen directly (main.c:154-160): HSL round trip with unit gains == identity
-                finished = true; out_L = m.emission; out_alb = m.emission; out_nrm = n;
-            } else {
-                const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 1u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
-                const float3 d_in = P.d;
-                P.o = hp;                                                                                 // main.c:162
-                P.src_prim = hit.prim; P.src_twin = twin;
-                const float3 diffuse_dir = normalize3(n + unit_sphere(u01(r.x), u01(r.y)));               // main.c:163
-                const float3 mirror_dir = reflect3(d_in, n);
-                const float3 mixed = lerp3(diffuse_dir, mirror_dir, m.reflection);                        // main.c:165
-                bool shade = true;
-                if (m.alpha <= 0.99f && m.alpha >= 0.0001f) {                                             // main.c:167-193
-                    float3 nn = n;
-                    float n1 = P.cur_index, n2 = m.index;                  // entering: (top.n2, m), push
-                    const float before = P.cur_index;
-                    P.cur_index = m.index;
-                    if (dot3(d_in, n) > 0.0f) {                            // leaving: pop, swap
-                        nn = -n; n1 = m.index; n2 = before; P.cur_index = before;
-                    }
-                    const float3 refr = refract3(d_in, nn, n1, n2);
-                    const uint4 rc = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 2u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
-                    if (u01(rc.x) > m.alpha) { P.d = refr; shade = false; }
-                    else P.d = mixed;
-                }
-                if (m.alpha > 0.99f) { P.is_alpha = false; P.d = mixed; }                                 // main.c:195-198
-                if (shade && m.alpha < 0.0001f) { P.is_alpha = true; P.alpha_depth++; shade = false; }    // main.c:200-206
-                P.bounce = i + 1;
-                if (shade) {
-                    const float k = A.use_ao ? A.emit_scale_ao : 1.0f;                                    // 1.5 * AO (main.c:210)
-                    P.L = P.L + (m.emission * (m.emission_strength * k)) * P.T;
-                    if (P.T.x > 0.5f || P.T.y > 0.5f || P.T.z > 0.5f) P.T = m.diffuse * (P.T * 1.3f);     // main.c:214-216
-                    P.T = m.diffuse * P.T;
-                    if (A.use_ao) {
-                        P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                         // main.c:100-102
-                        phase = PH_AO;
-                    }
-                }
-                out_L = P.L;
-                if (phase != PH_AO && P.bounce >= A.bounces) finished = true;
-            }
-        }
-
-        if (finished) {
-            acc[0] += to_fixed(out_L.x);   acc[1] += to_fixed(out_L.y);   acc[2] += to_fixed(out_L.z);
-            acc[3] += to_fixed(out_alb.x); acc[4] += to_fixed(out_alb.y); acc[5] += to_fixed(out_alb.z);
-            acc[6] += to_fixed(out_nrm.x); acc[7] += to_fixed(out_nrm.y); acc[8] += to_fixed(out_nrm.z);
-            s_cur++;
-            phase = PH_NEW;
         }
     }
 
@@ -300,24 +336,25 @@ resolve_kernel(ResolveArgs R)
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE = 0>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
 {
-    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT><<<grid, PT_THREADS, smem, stream>>>(A);
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, MODE><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 
-cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, bool brute, bool count_tests, cudaStream_t stream)
+cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream)
 {
-    const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4);
-    const int grid = n_sms * 2;
+    const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4) + sizeof(long long) * 9 * PT_THREADS;
+    const int grid = n_sms * (blocks_per_sm > 0 ? blocks_per_sm : 2);
     const bool has_tris = A.scene.n_tris > 0;
     if (!has_tris) return count_tests ? launch_variant<false, false, true>(A, grid, smem, stream)
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
-    return count_tests ? launch_variant<true, false, true>(A, grid, smem, stream)
-                       : launch_variant<true, false, false>(A, grid, smem, stream);
+    if (count_tests) return launch_variant<true, false, true>(A, grid, smem, stream);
+    return A.vote ? launch_variant<true, false, false, 1>(A, grid, smem, stream)
+                  : launch_variant<true, false, false, 0>(A, grid, smem, stream);
 }
 
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream)

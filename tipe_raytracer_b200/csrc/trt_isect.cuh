@@ -15,16 +15,10 @@
 #include "trt_device.cuh"
 
 #define TRT_NO_PRIM (-1)
-#define TRT_STACK_DEPTH 64
+#define TRT_STACK_DEPTH 68
 
 struct Ray {
     float3 o, d;
-};
-
-struct HitRec {
-    float t;        // in units of |d|; +inf when nothing was hit
-    int   prim;     // TRT_NO_PRIM, sphere k -> k, triangle at leaf position p -> n_spheres + p
-    float u, v;     // Moller-Trumbore barycentrics of the winning triangle (weights of B and C)
 };
 
 struct TraceCounters {
@@ -68,110 +62,126 @@ __device__ __forceinline__ bool triangle_test(float4 r0, float4 r1, float4 r2, f
     return det >= 1e-6f && t >= tmin && u >= 1e-7f && v >= 1e-7f && w >= 1e-7f;
 }
 
-// closest_hit (main.c:52-92): spheres in order, then triangles; strict '<' keeps the first
-// primitive on exact ties (for triangles: the lower index in the caller's array).
+// ---- resumable closest-hit query ------------------------------------------------------------------
+// closest_hit (main.c:52-92): spheres in order, then triangles; strict '<' keeps the first primitive
+// on exact ties (for triangles: the lower index in the caller's array).
+// The query is split so that a warp can leave the BVH loop while some lanes are still inside it:
+//   ray_begin  : the sphere scan (uniform trip count, no divergence) + traversal set-up
+//   bvh_step   : one node visit or one leaf test; state lives in Trav + the lane's local stack
+#define TRT_TRAV_DONE 0x7fffffff
+
+struct Trav {
+    int   node;     // TRT_TRAV_DONE when the query is complete; >= 0 internal node; < 0 leaf ~p
+    int   sp;       // stack pointer (stack[0] holds TRT_TRAV_DONE)
+    float t;        // best distance so far, in units of |d|
+    int   prim;     // TRT_NO_PRIM, sphere k -> k, triangle at leaf position p -> n_spheres + p
+    float u, v;     // Moller-Trumbore barycentrics of the best triangle (weights of B and C)
+};
+
+__device__ __forceinline__ float3 safe_inverse(float3 d)
+{
+    const float e = 1e-30f;
+    return f3(1.0f / (fabsf(d.x) > e ? d.x : copysignf(e, d.x)),
+              1.0f / (fabsf(d.y) > e ? d.y : copysignf(e, d.y)),
+              1.0f / (fabsf(d.z) > e ? d.z : copysignf(e, d.z)));
+}
+
 // any_hit: the caller only needs "hit anything" (ambient_occlusion, main.c:104-106).
 template <bool HAS_TRIS, bool BRUTE, bool COUNT>
-__device__ __forceinline__ HitRec trace_ray(const DevScene& sc, const float4* __restrict__ s_sph,
-                                            float3 o, float3 d, int src_prim, int src_twin, bool any_hit,
-                                            TraceCounters& cnt)
+__device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __restrict__ s_sph, float3 o, float3 d,
+                                          int src_prim, int src_twin, bool any_hit, Trav& tr, int* stack, TraceCounters& cnt)
 {
-    HitRec best;
-    best.t = __int_as_float(0x7f800000);
-    best.prim = TRT_NO_PRIM;
-    best.u = best.v = 0.0f;
-
+    tr.t = __int_as_float(0x7f800000);
+    tr.prim = TRT_NO_PRIM;
+    tr.u = tr.v = 0.0f;
+    tr.node = TRT_TRAV_DONE;
+    tr.sp = 0;
     const float a = dot3(d, d);
     const int ns = sc.n_spheres;
     for (int k = 0; k < ns; k++) {
         const float t = sphere_root(s_sph[k], o, d, a, k == src_prim);
-        if (t >= 0.0f && t < best.t) { best.t = t; best.prim = k; }
+        if (t >= 0.0f && t < tr.t) { tr.t = t; tr.prim = k; }
     }
     if (COUNT) cnt.sphere_tests += ns;
-
-    if (!HAS_TRIS || sc.n_tris == 0) return best;
-    if (any_hit && best.prim != TRT_NO_PRIM) return best;
-
-    const int src_leaf = src_prim - ns, twin_leaf = src_twin;      // leaf positions to skip (negative: none)
-    const float tmin = sc.tri_tmin;
-
+    if (!HAS_TRIS || sc.n_tris == 0) return;
+    if (any_hit && tr.prim != TRT_NO_PRIM) return;
     if (BRUTE) {
-        // linear scan in the caller's order, like main.c:81-90
+        // linear scan like main.c:81-90 (leaf order; ties resolved by the caller's index)
+        const int src_leaf = src_prim - ns;
         for (int p = 0; p < sc.n_tris; p++) {
-            if (p == src_leaf || p == twin_leaf) continue;
+            if (p == src_leaf || p == src_twin) continue;
             float t, u, v;
             const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
             if (COUNT) cnt.tri_tests++;
-            if (triangle_test(r0, r1, r2, o, d, tmin, t, u, v)) {
-                bool take = t < best.t;
-                if (t == best.t && best.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (best.prim - ns));
-                if (take) { best.t = t; best.prim = ns + p; best.u = u; best.v = v; }
+            if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
+                bool take = t < tr.t;
+                if (t == tr.t && tr.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (tr.prim - ns));
+                if (take) { tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v; }
             }
         }
-        return best;
+        return;
     }
+    stack[0] = TRT_TRAV_DONE;
+    tr.sp = 1;
+    tr.node = sc.root;
+}
 
-    // ---- BVH2 traversal, stack in local memory --------------------------------------------
-    const float ooeps = 1e-30f;
-    const float3 idir = f3(1.0f / (fabsf(d.x) > ooeps ? d.x : copysignf(ooeps, d.x)),
-                           1.0f / (fabsf(d.y) > ooeps ? d.y : copysignf(ooeps, d.y)),
-                           1.0f / (fabsf(d.z) > ooeps ? d.z : copysignf(ooeps, d.z)));
-    const float3 ood = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-
-    int stack[TRT_STACK_DEPTH];
-    int sp = 0;
-    int node = sc.root;
-    const int SENTINEL = 0x7fffffff;
-    stack[sp++] = SENTINEL;
-
-    while (node != SENTINEL) {
-        while (node >= 0 && node != SENTINEL) {
-            const float4 n0 = __ldg(sc.nodes + 4 * node), n1 = __ldg(sc.nodes + 4 * node + 1);
-            const float4 n2 = __ldg(sc.nodes + 4 * node + 2);
-            const int4 ch = __ldg((const int4*)(sc.nodes + 4 * node + 3));
-            if (COUNT) cnt.box_tests += 2;
-            // child 0: x in (n0.x, n0.y), y in (n0.z, n0.w), z in (n2.x, n2.y)
-            const float c0lox = fmaf(n0.x, idir.x, -ood.x), c0hix = fmaf(n0.y, idir.x, -ood.x);
-            const float c0loy = fmaf(n0.z, idir.y, -ood.y), c0hiy = fmaf(n0.w, idir.y, -ood.y);
-            const float c0loz = fmaf(n2.x, idir.z, -ood.z), c0hiz = fmaf(n2.y, idir.z, -ood.z);
-            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), best.t));
-            // child 1: x in (n1.x, n1.y), y in (n1.z, n1.w), z in (n2.z, n2.w)
-            const float c1lox = fmaf(n1.x, idir.x, -ood.x), c1hix = fmaf(n1.y, idir.x, -ood.x);
-            const float c1loy = fmaf(n1.z, idir.y, -ood.y), c1hiy = fmaf(n1.w, idir.y, -ood.y);
-            const float c1loz = fmaf(n2.z, idir.z, -ood.z), c1hiz = fmaf(n2.w, idir.z, -ood.z);
-            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), best.t));
-            const bool h0 = c0max >= c0min, h1 = c1max >= c1min;
-            if (!h0 && !h1) { node = stack[--sp]; }
-            else {
-                node = h0 ? ch.x : ch.y;
-                if (h0 && h1) {
-                    int far = ch.y;
-                    if (c1min < c0min) { far = ch.x; node = ch.y; }
-                    if (sp < TRT_STACK_DEPTH) stack[sp++] = far;
-                }
-            }
+// One internal-node visit for a lane with tr.node >= 0 (and != TRT_TRAV_DONE).
+template <bool COUNT>
+__device__ __forceinline__ void bvh_visit(const DevScene& sc, float3 idir, float3 ood, Trav& tr, int* stack, TraceCounters& cnt)
+{
+    const int node = tr.node;
+    const float4 n0 = __ldg(sc.nodes + 4 * node), n1 = __ldg(sc.nodes + 4 * node + 1);
+    const float4 n2 = __ldg(sc.nodes + 4 * node + 2);
+    const int4 ch = __ldg((const int4*)(sc.nodes + 4 * node + 3));
+    if (COUNT) cnt.box_tests += 2;
+    // child 0: x in (n0.x, n0.y), y in (n0.z, n0.w), z in (n2.x, n2.y)
+    const float c0lox = fmaf(n0.x, idir.x, -ood.x), c0hix = fmaf(n0.y, idir.x, -ood.x);
+    const float c0loy = fmaf(n0.z, idir.y, -ood.y), c0hiy = fmaf(n0.w, idir.y, -ood.y);
+    const float c0loz = fmaf(n2.x, idir.z, -ood.z), c0hiz = fmaf(n2.y, idir.z, -ood.z);
+    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tr.t));
+    // child 1: x in (n1.x, n1.y), y in (n1.z, n1.w), z in (n2.z, n2.w)
+    const float c1lox = fmaf(n1.x, idir.x, -ood.x), c1hix = fmaf(n1.y, idir.x, -ood.x);
+    const float c1loy = fmaf(n1.z, idir.y, -ood.y), c1hiy = fmaf(n1.w, idir.y, -ood.y);
+    const float c1loz = fmaf(n2.z, idir.z, -ood.z), c1hiz = fmaf(n2.w, idir.z, -ood.z);
+    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tr.t));
+    const bool h0 = c0max >= c0min, h1 = c1max >= c1min;
+    if (!h0 && !h1) { tr.node = stack[--tr.sp]; }
+    else {
+        int next = h0 ? ch.x : ch.y;
+        if (h0 && h1) {
+            int far = ch.y;
+            if (c1min < c0min) { far = ch.x; next = ch.y; }
+            if (tr.sp < TRT_STACK_DEPTH) stack[tr.sp++] = far;
         }
-        if (node == SENTINEL) break;
-        // leaf: one triangle at leaf position ~node
-        const int p = ~node;
-        if (p != src_leaf && p != twin_leaf) {
-            float t, u, v;
-            const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
-            if (COUNT) cnt.tri_tests++;
-            if (triangle_test(r0, r1, r2, o, d, tmin, t, u, v)) {
-                bool take = t < best.t;
-                if (t == best.t && best.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (best.prim - ns));
-                if (take) {
-                    best.t = t; best.prim = ns + p; best.u = u; best.v = v;
-                    if (any_hit) break;
-                }
-            }
-        }
-        node = stack[--sp];
+        tr.node = next;
     }
-    return best;
+}
+
+// One leaf test for a lane with tr.node < 0: the triangle at leaf position ~node.
+template <bool COUNT>
+__device__ __forceinline__ void bvh_leaf(const DevScene& sc, float3 o, float3 d, int src_leaf, int twin_leaf, bool any_hit,
+                                         Trav& tr, int* stack, TraceCounters& cnt)
+{
+    const int p = ~tr.node;
+    int next = stack[--tr.sp];
+    if (p != src_leaf && p != twin_leaf) {
+        float t, u, v;
+        const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+        if (COUNT) cnt.tri_tests++;
+        if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
+            const int ns = sc.n_spheres;
+            bool take = t < tr.t;
+            if (t == tr.t && tr.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (tr.prim - ns));
+            if (take) {
+                tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
+                if (any_hit) next = TRT_TRAV_DONE;
+            }
+        }
+    }
+    tr.node = next;
 }
 
 // ---- material at the hit ----------------------------------------------------------------------

@@ -24,6 +24,7 @@ struct RenderArgs {
     uint32_t key0, key1;
     // work decomposition
     int chunk, n_chunks, tiles_x, tiles_y;
+    int min_steps, exit_num, vote;      // BVH-loop policy, see pathtrace.cu
     long long n_items;
     unsigned long long* item_counter;   // zeroed before launch
     unsigned long long* counters;       // [0] rays [1] box tests [2] triangle tests [3] sphere tests
@@ -36,7 +37,7 @@ struct ResolveArgs {
     double *canva, *albedo, *normal;    // [W*H][3]
 };
 
-cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, bool brute, bool count_tests, cudaStream_t stream);
+cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream);
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
 
 // K1: FP64 primary visibility, linear scan in the caller's order.
