@@ -32,6 +32,8 @@ struct DeviceCtx {
     unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
     unsigned long long* h_ctrs = nullptr;      // pinned mirror
     long long* accum = nullptr; size_t accum_px = 0;
+    void* wf_buf = nullptr; size_t wf_bytes = 0;   // wavefront slot state
+    int last_launches = 0;
     double* out = nullptr; size_t out_px = 0;  // canva | albedo | normal, each [npix][3]
 };
 
@@ -128,11 +130,19 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.key0 = (uint32_t)(p->seed & 0xffffffffu); A.key1 = (uint32_t)(p->seed >> 32);
     // tuning knobs (defaults chosen from measurements on B200); env overrides are for experiments
     auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
-    const int chunk_max = knob("TRT_TUNE_CHUNK", 32);
-    A.min_steps = knob("TRT_TUNE_MIN_STEPS", 8);
-    A.exit_num = knob("TRT_TUNE_EXIT", 20);
+    const bool brute = (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, count_tests = (p->flags & TRT_FLAG_COUNT_TESTS) != 0;
+    // engine: triangles => wavefront (small high-occupancy query kernel), spheres only => register-resident megakernel
+    int engine = knob("TRT_ENGINE", 0);
+    if (engine == 0) engine = (d.scene.n_tris > 0 && !brute && p->nbRebondMax <= 8191) ? 2 : 1;
+    if (engine == 2 && (brute || p->nbRebondMax > 8191)) engine = 1;
+    const int chunk_max = engine == 2 ? knob("TRT_TUNE_WF_CHUNK", 16) : knob("TRT_TUNE_CHUNK", 32);
+    A.min_steps = knob("TRT_TUNE_MIN_STEPS", engine == 2 ? 4 : 8);
+    A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 16);
     A.vote = knob("TRT_TUNE_VOTE", 0);
-    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 2);
+    A.count_tests = count_tests ? 1 : 0;
+    A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
+    A.wf_check = knob("TRT_TUNE_WF_CHECK", 8);
+    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (2 with triangles, 3 without)
     A.chunk = spp < chunk_max ? spp : chunk_max;
     A.n_chunks = (spp + A.chunk - 1) / A.chunk;
     A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;
@@ -141,10 +151,30 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.counters = d.ctrs + 1;
     A.accum = accum;
     CU(ctx, cudaMemsetAsync(d.ctrs, 0, sizeof(unsigned long long) * 8, d.stream));
-    CU(ctx, cudaEventRecord(d.ev_a, d.stream));
-    CU(ctx, trt_launch_pathtrace(A, d.n_sms, blocks_per_sm, (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, (p->flags & TRT_FLAG_COUNT_TESTS) != 0, d.stream));
-    CU(ctx, cudaEventRecord(d.ev_b, d.stream));
-    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 8, cudaMemcpyDeviceToHost, d.stream));
+    if (engine == 2) {
+        const long long real_items = (long long)A.W * A.H * A.n_chunks;
+        long long want = knob("TRT_TUNE_SLOTS", 1 << 20);
+        if (want > real_items) want = real_items;
+        const int n_slots = (int)(((want + 255) / 256) * 256);
+        const size_t bytes = trt_wavefront_bytes(n_slots);
+        if (d.wf_bytes < bytes) {
+            if (d.wf_buf) cudaFree(d.wf_buf);
+            d.wf_buf = nullptr; d.wf_bytes = 0;
+            CU(ctx, cudaMalloc(&d.wf_buf, bytes));
+            d.wf_bytes = bytes;
+        }
+        WfState S{};
+        trt_wavefront_carve(d.wf_buf, n_slots, S);
+        CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+        CU(ctx, trt_launch_wavefront(A, S, d.n_sms, (int*)&d.h_ctrs[7], &d.last_launches, d.stream));
+        CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+    } else {
+        CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+        CU(ctx, trt_launch_pathtrace(A, d.n_sms, blocks_per_sm, brute, count_tests, d.stream));
+        CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+        d.last_launches = 1;
+    }
+    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 7, cudaMemcpyDeviceToHost, d.stream));
     return TRT_OK;
 }
 
@@ -252,6 +282,7 @@ TRT_API void trt_destroy(trt_ctx* ctx)
         if (d.stream) cudaStreamSynchronize(d.stream);
         free_scene(d);
         if (d.accum) cudaFree(d.accum);
+        if (d.wf_buf) cudaFree(d.wf_buf);
         if (d.out) cudaFree(d.out);
         if (d.ctrs) cudaFree(d.ctrs);
         if (d.h_ctrs) cudaFreeHost(d.h_ctrs);
@@ -312,7 +343,7 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
         CU(ctx, cudaMalloc(&d.tri, sizeof(float4) * 3 * nt));
         CU(ctx, cudaMalloc(&d.tri_uv, sizeof(float4) * 2 * nt));
         CU(ctx, cudaMalloc(&d.tri_orig, sizeof(int) * nt));
-        CU(ctx, cudaMalloc(&d.nodes, sizeof(float4) * 4 * nt));
+        CU(ctx, cudaMalloc(&d.nodes, sizeof(float4) * 8 * nt));
         CU(ctx, cudaMalloc(&d.texels, sizeof(float4) * 3 * (n_texels > 0 ? n_texels : 1)));
         if (nbSpheres) CU(ctx, cudaMemcpyAsync(d.sph_raw, sphere_list, sizeof(trt_sphere) * nbSpheres, cudaMemcpyHostToDevice, d.stream));
         if (nbTriangles) {
@@ -345,8 +376,10 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
         s.quel_mat = d.quel_mat; s.nodes = d.nodes; s.root = bo.root;
         s.texels = d.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
         s.tri_tmin = bo.tri_tmin;
+        if (3 * bo.max_depth + 2 > TRT_STACK_DEPTH)
+            return fail(ctx, TRT_ERR_INVALID, "BVH depth %d needs a traversal stack of %d entries (limit %d)", bo.max_depth, 3 * bo.max_depth + 2, TRT_STACK_DEPTH);
         if (&d == &ctx->devs[0]) {
-            ctx->info.n_nodes = nbTriangles > 1 ? nbTriangles - 1 : 0;
+            ctx->info.n_nodes = bo.n_wide_nodes;
             ctx->info.n_leaves = nbTriangles;
             ctx->info.max_depth = bo.max_depth; ctx->info.n_twins = bo.n_twins; ctx->info.sah_cost = bo.sah_cost;
         }
@@ -379,7 +412,7 @@ TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_ac
     if (stats) {
         memset(stats, 0, sizeof *stats);
         collect_stats(ctx, params, stats, true);
-        stats->kernel_launches = 1;
+        stats->kernel_launches = d.last_launches;
         stats->ms_total = now_ms() - t0;
     }
     return TRT_OK;
@@ -454,7 +487,7 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
         CU(ctx, cudaMemsetAsync(d.accum, 0, sizeof(long long) * 9 * npix, d.stream));
         if (s1 > s0) {
             if ((rc = launch_trace(ctx, d, params, s1 - s0, params->sample_offset + s0, d.accum)) != TRT_OK) return rc;
-            launches++;
+            launches += d.last_launches;
         } else {
             CU(ctx, cudaEventRecord(d.ev_a, d.stream));
             CU(ctx, cudaEventRecord(d.ev_b, d.stream));

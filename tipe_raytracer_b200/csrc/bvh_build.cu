@@ -13,7 +13,10 @@
 //                      are neighbours after the sort; each records the other's leaf position
 //   6. build_hierarchy Karras 2012: one thread per internal node, longest-common-prefix ranges
 //   7. refit           bottom-up boxes, second arriver at each node continues (atomic flags)
-//   8. write_nodes     64-byte nodes with both child boxes inline + SAH cost reduction
+//   8. sah_cost        surface-area cost of the binary tree (reported through trt_bvh_info)
+//   9. collapse_level  binary -> 4-wide: each surviving node adopts its grandchildren, largest box first,
+//                      until it has 4 children; one launch per level of the wide tree.  128-byte nodes
+//                      (one L1 line): 4 child boxes as 6 float4 (SoA) + int4 child references
 #include <cub/device/device_radix_sort.cuh>
 
 #include "trt_kernels.h"
@@ -245,27 +248,64 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi)
     return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void write_nodes(int n, const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                            const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, float4* nodes, double* sah)
+__global__ void sah_cost_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, double* sah)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
     if (i < n - 1) {
         const int2 ch = children[i];
-        const float4 alo = ch.x < 0 ? leaf_lo[~ch.x] : node_lo[ch.x], ahi = ch.x < 0 ? leaf_hi[~ch.x] : node_hi[ch.x];
-        const float4 blo = ch.y < 0 ? leaf_lo[~ch.y] : node_lo[ch.y], bhi = ch.y < 0 ? leaf_hi[~ch.y] : node_hi[ch.y];
-        nodes[4 * i + 0] = make_float4(alo.x, ahi.x, alo.y, ahi.y);
-        nodes[4 * i + 1] = make_float4(blo.x, bhi.x, blo.y, bhi.y);
-        nodes[4 * i + 2] = make_float4(alo.z, ahi.z, blo.z, bhi.z);
-        nodes[4 * i + 3] = make_float4(__int_as_float(ch.x), __int_as_float(ch.y), 0.0f, 0.0f);
         // SAH with C_box = 1 per child box test and C_tri = 1 per leaf, relative to the root area
         const float root_area = fmaxf(half_area(node_lo[0], node_hi[0]), 1e-30f);
         cost = (double)(half_area(node_lo[i], node_hi[i]) / root_area) * 2.0;
-        if (ch.x < 0) cost += (double)(half_area(alo, ahi) / root_area);
-        if (ch.y < 0) cost += (double)(half_area(blo, bhi) / root_area);
+        if (ch.x < 0) cost += (double)(half_area(leaf_lo[~ch.x], leaf_hi[~ch.x]) / root_area);
+        if (ch.y < 0) cost += (double)(half_area(leaf_lo[~ch.y], leaf_hi[~ch.y]) / root_area);
     }
     for (int off = 16; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
     if ((threadIdx.x & 31) == 0 && cost != 0.0) atomicAdd(sah, cost);
+}
+
+// One level of the binary -> 4-wide collapse.  q_in[k] = (binary node, wide node index to fill).
+// counters[0] = wide nodes allocated so far, counters[1] = entries written to q_out.
+__global__ void collapse_level(const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                               const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                               const int2* __restrict__ q_in, int n_in, int2* q_out, int* counters, float4* nodes4)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_in) return;
+    const int2 e = q_in[k];
+    int c[4]; int nc = 2;
+    { const int2 ch = children[e.x]; c[0] = ch.x; c[1] = ch.y; c[2] = c[3] = 0; }
+    while (nc < 4) {
+        int best = -1; float best_area = -1.0f;
+        for (int j = 0; j < nc; j++)
+            if (c[j] >= 0) { const float a = half_area(node_lo[c[j]], node_hi[c[j]]); if (a > best_area) { best_area = a; best = j; } }
+        if (best < 0) break;
+        const int2 ch = children[c[best]];
+        c[best] = ch.x; c[nc++] = ch.y;
+    }
+    float lo[3][4], hi[3][4]; int ref[4];
+    for (int j = 0; j < 4; j++) {
+        if (j < nc) {
+            const float4 l = c[j] < 0 ? leaf_lo[~c[j]] : node_lo[c[j]], h = c[j] < 0 ? leaf_hi[~c[j]] : node_hi[c[j]];
+            lo[0][j] = l.x; lo[1][j] = l.y; lo[2][j] = l.z; hi[0][j] = h.x; hi[1][j] = h.y; hi[2][j] = h.z;
+            if (c[j] < 0) ref[j] = c[j];
+            else {
+                const int idx = atomicAdd(counters + 0, 1);
+                ref[j] = idx;
+                q_out[atomicAdd(counters + 1, 1)] = make_int2(c[j], idx);
+            }
+        } else {
+            for (int a = 0; a < 3; a++) { lo[a][j] = 0.0f; hi[a][j] = 0.0f; }
+            ref[j] = 0x7ffffffe;                                  // TRT_CHILD_EMPTY
+        }
+    }
+    float4* out = nodes4 + 8 * (size_t)e.y;
+    out[0] = make_float4(lo[0][0], lo[0][1], lo[0][2], lo[0][3]); out[1] = make_float4(hi[0][0], hi[0][1], hi[0][2], hi[0][3]);
+    out[2] = make_float4(lo[1][0], lo[1][1], lo[1][2], lo[1][3]); out[3] = make_float4(hi[1][0], hi[1][1], hi[1][2], hi[1][3]);
+    out[4] = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); out[5] = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
+    out[6] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
+    out[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 struct Scratch {
@@ -282,6 +322,7 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream)
 {
     out.root = 0; out.max_depth = 0; out.n_twins = 0; out.sah_cost = 0.0; out.tri_tmin = 1e-7f;
+    out.n_wide_nodes = 0; out.wide_depth = 0; out.binary_depth = 0;
     const int TB = 256;
 
     if (in.n_spheres > 0) {
@@ -310,6 +351,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     const size_t o_keys_a = take(sizeof(unsigned long long) * n), o_keys_b = take(sizeof(unsigned long long) * n);
     const size_t o_children = take(sizeof(int2) * n), o_parent_node = take(sizeof(int) * n), o_parent_leaf = take(sizeof(int) * n);
     const size_t o_flags = take(sizeof(int) * n);
+    const size_t o_queue_a = take(sizeof(int2) * n), o_queue_b = take(sizeof(int2) * n);
     const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64)
     const size_t o_cub = take(cub_bytes);
     Scratch scratch;
@@ -352,19 +394,41 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, small + 9);
     BT(cudaGetLastError());
     if (n == 1) {
-        out.root = ~0; out.max_depth = 1;
+        out.root = ~0; out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;
     } else {
         build_hierarchy<<<grid_n, TB, 0, stream>>>(n, keys_b, children, parent_node, parent_leaf);
         refit<<<grid_n, TB, 0, stream>>>(n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, small + 8);
-        write_nodes<<<grid_n, TB, 0, stream>>>(n, children, leaf_lo, leaf_hi, node_lo, node_hi, out.nodes, sah);
+        sah_cost_kernel<<<grid_n, TB, 0, stream>>>(n, children, leaf_lo, leaf_hi, node_lo, node_hi, sah);
         BT(cudaGetLastError());
+        // binary -> 4-wide, one launch per level (the queue sizes come back to the host: ~depth/2 round trips)
+        int2* q[2] = {(int2*)(base + o_queue_a), (int2*)(base + o_queue_b)};
+        int* counters = small + 24;
+        const int2 root_entry = make_int2(0, 0);
+        int h_counters[2] = {1, 0};
+        BT(cudaMemcpyAsync(q[0], &root_entry, sizeof(int2), cudaMemcpyHostToDevice, stream));
+        BT(cudaMemcpyAsync(counters, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, stream));
+        int n_in = 1, level = 0;
+        while (n_in > 0) {
+            collapse_level<<<(n_in + TB - 1) / TB, TB, 0, stream>>>(children, leaf_lo, leaf_hi, node_lo, node_hi,
+                                                                   q[level & 1], n_in, q[(level + 1) & 1], counters, out.nodes);
+            BT(cudaGetLastError());
+            BT(cudaMemcpyAsync(h_counters, counters, sizeof h_counters, cudaMemcpyDeviceToHost, stream));
+            BT(cudaStreamSynchronize(stream));
+            n_in = h_counters[1];
+            h_counters[1] = 0;
+            BT(cudaMemcpyAsync(counters + 1, h_counters + 1, sizeof(int), cudaMemcpyHostToDevice, stream));
+            level++;
+        }
+        out.n_wide_nodes = h_counters[0];
+        out.wide_depth = level;
         out.root = 0;
     }
     int h_tail[2]; double h_sah = 0.0;
     BT(cudaMemcpyAsync(h_tail, small + 8, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
     BT(cudaMemcpyAsync(&h_sah, sah, sizeof(double), cudaMemcpyDeviceToHost, stream));
     BT(cudaStreamSynchronize(stream));
-    if (n > 1) out.max_depth = h_tail[0];
+    if (n > 1) out.binary_depth = h_tail[0];
+    out.max_depth = n > 1 ? out.wide_depth + 1 : 1;
     out.n_twins = h_tail[1];
     out.sah_cost = h_sah;
     return cudaSuccess;

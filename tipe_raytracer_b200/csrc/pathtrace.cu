@@ -16,8 +16,7 @@
 //     schedule, any grid and any split of the samples over GPUs;
 //   * spheres (and their materials) are staged once per CTA into shared memory; BVH nodes,
 //     triangles and texels are read through the read-only path and live in L1/L2.
-#include "trt_isect.cuh"
-#include "trt_kernels.h"
+#include "trt_shade.cuh"
 
 #define PT_THREADS 256
 #define PT_POOL 32
@@ -25,22 +24,8 @@
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
-struct PathState {
-    float3 o, d;            // current ray (d is NOT normalised after a mirror/diffuse lerp, main.c:165)
-    float3 d_ao;            // pending ambient-occlusion direction
-    float3 T, L;            // rayColor, incomingLight (main.c:120-121)
-    float3 aov_albedo, aov_normal;
-    float  cur_index;       // the refraction stack collapsed to its top n2 (pile.h)
-    int    bounce;          // i of main.c:132
-    int    alpha_depth;
-    int    src_prim, src_twin;
-    bool   is_alpha;
-};
-
-enum { PH_NEW = 0, PH_BOUNCE = 1, PH_AO = 2, PH_DONE = 3 };
-
 template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE>
-__global__ void __launch_bounds__(PT_THREADS, 2)
+__global__ void __launch_bounds__(PT_THREADS, HAS_TRIS ? 2 : 3)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
     extern __shared__ float4 smem[];
@@ -80,98 +65,15 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
 
         // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
         if (tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)) {
-            bool finished = false;          // path ended
-            float3 out_L = P.L, out_alb = P.aov_albedo, out_nrm = P.aov_normal;
-            const bool did_hit = tr.prim != TRT_NO_PRIM;
-
-            if (phase == PH_AO) {
-                // ambient_occlusion (main.c:94-116): distance/dst == 1 for a unit direction, so the term
-                // is 1/AO when anything is hit and 0 otherwise.
-                P.T = P.T * (did_hit ? A.inv_ao : 0.0f);
-                if (P.bounce >= A.bounces) finished = true;
-                else { phase = PH_BOUNCE; new_ray = true; }
-            } else {
-                const int i = P.bounce;
-                Material m;
-                float3 n = f3(0, 0, 0), hp = P.o;
-                int twin = -1;
-                if (did_hit) {
-                    hp = fma3(P.d, tr.t, P.o);
-                    if (tr.prim < sc.n_spheres) {
-                        const float4 cr = s_sph[tr.prim];
-                        n = normalize3(hp - xyz(cr));                                    // sphere.h:33 (always outward)
-                        m = unpack_material(s_mat[3 * tr.prim], s_mat[3 * tr.prim + 1], s_mat[3 * tr.prim + 2]);
-                    } else {
-                        const int leaf = tr.prim - sc.n_spheres;
-                        const float4 r2 = __ldg(sc.tri + 3 * leaf + 2);
-                        n = normalize3(f3(r2.y, r2.z, r2.w));                            // mesh.h:90
-                        m = triangle_material(sc, leaf, tr.u, tr.v, twin);
-                    }
-                } else {
-                    // the reference reads an uninitialised HitInfo here (main.c:135-139); defined as zeros
-                    m = unpack_material(make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0));
-                }
-
-                if (i == 0) { P.aov_albedo = m.diffuse; P.aov_normal = n; }                                   // main.c:137-140
-                if (i == P.alpha_depth && P.is_alpha) {                                                       // main.c:142-150
-                    P.aov_albedo = (m.emission_strength > 0.0f) ? m.emission : m.diffuse;
-                    P.aov_normal = n;
-                    P.is_alpha = false;
-                }
-                out_alb = P.aov_albedo; out_nrm = P.aov_normal;
-
-                if (!did_hit) {
-                    finished = true;                                                                          // main.c:236-238
-                } else if (i == P.alpha_depth && m.emission_strength > 0.0f) {
-                    // light seen directly (main.c:154-160): HSL round trip with unit gains == identity
-                    finished = true; out_L = m.emission; out_alb = m.emission; out_nrm = n;
-                } else {
-                    const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 1u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
-                    const float3 d_in = P.d;
-                    P.o = hp;                                                                                 // main.c:162
-                    P.src_prim = tr.prim; P.src_twin = twin;
-                    const float3 diffuse_dir = normalize3(n + unit_sphere(u01(r.x), u01(r.y)));               // main.c:163
-                    const float3 mirror_dir = reflect3(d_in, n);
-                    const float3 mixed = lerp3(diffuse_dir, mirror_dir, m.reflection);                        // main.c:165
-                    bool shade = true;
-                    if (m.alpha <= 0.99f && m.alpha >= 0.0001f) {                                             // main.c:167-193
-                        float3 nn = n;
-                        float n1 = P.cur_index, n2 = m.index;                  // entering: (top.n2, m), push
-                        const float before = P.cur_index;
-                        P.cur_index = m.index;
-                        if (dot3(d_in, n) > 0.0f) {                            // leaving: pop, swap
-                            nn = -n; n1 = m.index; n2 = before; P.cur_index = before;
-                        }
-                        const float3 refr = refract3(d_in, nn, n1, n2);
-                        const uint4 rc = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 2u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
-                        if (u01(rc.x) > m.alpha) { P.d = refr; shade = false; }
-                        else P.d = mixed;
-                    }
-                    if (m.alpha > 0.99f) { P.is_alpha = false; P.d = mixed; }                                 // main.c:195-198
-                    if (shade && m.alpha < 0.0001f) { P.is_alpha = true; P.alpha_depth++; shade = false; }    // main.c:200-206
-                    P.bounce = i + 1;
-                    if (shade) {
-                        const float k = A.use_ao ? A.emit_scale_ao : 1.0f;                                    // 1.5 * AO (main.c:210)
-                        P.L = P.L + (m.emission * (m.emission_strength * k)) * P.T;
-                        if (P.T.x > 0.5f || P.T.y > 0.5f || P.T.z > 0.5f) P.T = m.diffuse * (P.T * 1.3f);     // main.c:214-216
-                        P.T = m.diffuse * P.T;
-                        if (A.use_ao) {
-                            P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                         // main.c:100-102
-                            phase = PH_AO;
-                        }
-                    }
-                    out_L = P.L;
-                    if (phase != PH_AO && P.bounce >= A.bounces) finished = true;
-                    else new_ray = true;
-                }
-            }
-            if (finished) {
-                my_acc[0 * PT_THREADS] += to_fixed(out_L.x);   my_acc[1 * PT_THREADS] += to_fixed(out_L.y);   my_acc[2 * PT_THREADS] += to_fixed(out_L.z);
-                my_acc[3 * PT_THREADS] += to_fixed(out_alb.x); my_acc[4 * PT_THREADS] += to_fixed(out_alb.y); my_acc[5 * PT_THREADS] += to_fixed(out_alb.z);
-                my_acc[6 * PT_THREADS] += to_fixed(out_nrm.x); my_acc[7 * PT_THREADS] += to_fixed(out_nrm.y); my_acc[8 * PT_THREADS] += to_fixed(out_nrm.z);
+            PathResult res;
+            if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res)) {
+                my_acc[0 * PT_THREADS] += to_fixed(res.L.x);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z);
+                my_acc[3 * PT_THREADS] += to_fixed(res.albedo.x); my_acc[4 * PT_THREADS] += to_fixed(res.albedo.y); my_acc[5 * PT_THREADS] += to_fixed(res.albedo.z);
+                my_acc[6 * PT_THREADS] += to_fixed(res.normal.x); my_acc[7 * PT_THREADS] += to_fixed(res.normal.y); my_acc[8 * PT_THREADS] += to_fixed(res.normal.z);
                 s_cur++;
                 phase = PH_NEW;
-                new_ray = false;
+            } else {
+                new_ray = true;
             }
         }
 
@@ -236,20 +138,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         // ---- A3. start a path: fill_canva's per-sample set-up (main.c:265-271) --------------------
         if (phase == PH_NEW && pixel >= 0 && s_cur < s_end && A.bounces <= 0) s_cur = s_end;   // main.c:132 never iterates: all sums stay 0
         if (phase == PH_NEW && pixel >= 0 && s_cur < s_end) {
-            const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + s_cur), 0u, 0u, A.key0, A.key1);
-            const float u = ((float)px + (u01(r.x) - 0.5f)) * A.inv_wm1;
-            const float v = ((float)py + (u01(r.y) - 0.5f)) * A.inv_hm1;
-            const float dx = (u01(r.z) - 0.5f) * A.aperture_x;
-            const float dy = (u01(r.w) - 0.5f) * A.aperture_y;
-            // get_ray (camera.h:42-54); A.cam_corner = coin_bas_gauche - origin, formed in FP64 on the host
-            const float3 direction = fma3(A.cam_hor, u, fma3(A.cam_ver, v, A.cam_corner));
-            const float3 dest = fma3(direction, A.focus, A.cam_origin);
-            P.o = f3(A.cam_origin.x + dx, A.cam_origin.y + dy, A.cam_origin.z);
-            P.d = normalize3(dest - P.o);
-            P.T = f3(1, 1, 1); P.L = f3(0, 0, 0);
-            P.aov_albedo = P.aov_normal = f3(0, 0, 0);
-            P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.is_alpha = false;
-            P.src_prim = TRT_NO_PRIM; P.src_twin = -1;
+            start_path(A, pixel, px, py, s_cur, P);
             phase = PH_BOUNCE;
             new_ray = true;
         }
@@ -346,7 +235,7 @@ static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cu
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream)
 {
     const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4) + sizeof(long long) * 9 * PT_THREADS;
-    const int grid = n_sms * (blocks_per_sm > 0 ? blocks_per_sm : 2);
+    const int grid = n_sms * (blocks_per_sm > 0 ? blocks_per_sm : (A.scene.n_tris > 0 ? 2 : 3));
     const bool has_tris = A.scene.n_tris > 0;
     if (!has_tris) return count_tests ? launch_variant<false, false, true>(A, grid, smem, stream)
                                       : launch_variant<false, false, false>(A, grid, smem, stream);

@@ -14,6 +14,8 @@
 #define TRT_SAMPLE_CLAMP 1048576.0f           /* |per-sample value| <= 2^20 before quantisation */
 
 #define TRT_MAX_SMEM_SPHERES 1024
+#define TRT_STACK_DEPTH 96                    /* traversal stack entries per lane (local memory) */
+#define TRT_CHILD_EMPTY 0x7ffffffe             /* unused child slot of a 4-wide node */
 
 // ---- device scene (all pointers are device pointers owned by the ctx) -----------------------
 struct DevScene {
@@ -29,8 +31,9 @@ struct DevScene {
     const int*    tri_orig;     // [n]   leaf position -> index in the caller's triangle array
     const double* tri64;        // raw copy of the caller's triangle array (200 B each), caller order
     const int*    quel_mat;     // [n]   caller order
-    // BVH2, 64-byte nodes with the two child boxes inline
-    const float4* nodes;        // [4*(n-1)]
+    // 4-wide BVH, 128-byte nodes (one L1 line): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] child[4] pad
+    // child reference: >= 0 wide node, < 0 leaf ~(leaf position), TRT_CHILD_EMPTY unused slot
+    const float4* nodes;
     int root;                   // 0, or ~0 when there is a single triangle
     // textures: nbMaterials slabs of tex_h*tex_w texels, 3 float4 per texel, overrides baked in
     const float4* texels;

@@ -15,7 +15,6 @@
 #include "trt_device.cuh"
 
 #define TRT_NO_PRIM (-1)
-#define TRT_STACK_DEPTH 68
 
 struct Ray {
     float3 o, d;
@@ -126,38 +125,52 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
     tr.node = sc.root;
 }
 
-// One internal-node visit for a lane with tr.node >= 0 (and != TRT_TRAV_DONE).
+// One visit of a 4-wide node for a lane with tr.node >= 0 (and != TRT_TRAV_DONE): four slab tests,
+// children that are hit are ordered by entry distance (5-comparator network), the nearest is
+// visited next and the others pushed farthest first.
+__device__ __forceinline__ void order2(float& ka, int& ra, float& kb, int& rb)
+{
+    const bool sw = kb < ka;
+    const float k0 = sw ? kb : ka, k1 = sw ? ka : kb;
+    const int r0 = sw ? rb : ra, r1 = sw ? ra : rb;
+    ka = k0; kb = k1; ra = r0; rb = r1;
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void bvh_visit(const DevScene& sc, float3 idir, float3 ood, Trav& tr, int* stack, TraceCounters& cnt)
 {
-    const int node = tr.node;
-    const float4 n0 = __ldg(sc.nodes + 4 * node), n1 = __ldg(sc.nodes + 4 * node + 1);
-    const float4 n2 = __ldg(sc.nodes + 4 * node + 2);
-    const int4 ch = __ldg((const int4*)(sc.nodes + 4 * node + 3));
-    if (COUNT) cnt.box_tests += 2;
-    // child 0: x in (n0.x, n0.y), y in (n0.z, n0.w), z in (n2.x, n2.y)
-    const float c0lox = fmaf(n0.x, idir.x, -ood.x), c0hix = fmaf(n0.y, idir.x, -ood.x);
-    const float c0loy = fmaf(n0.z, idir.y, -ood.y), c0hiy = fmaf(n0.w, idir.y, -ood.y);
-    const float c0loz = fmaf(n2.x, idir.z, -ood.z), c0hiz = fmaf(n2.y, idir.z, -ood.z);
-    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tr.t));
-    // child 1: x in (n1.x, n1.y), y in (n1.z, n1.w), z in (n2.z, n2.w)
-    const float c1lox = fmaf(n1.x, idir.x, -ood.x), c1hix = fmaf(n1.y, idir.x, -ood.x);
-    const float c1loy = fmaf(n1.z, idir.y, -ood.y), c1hiy = fmaf(n1.w, idir.y, -ood.y);
-    const float c1loz = fmaf(n2.z, idir.z, -ood.z), c1hiz = fmaf(n2.w, idir.z, -ood.z);
-    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tr.t));
-    const bool h0 = c0max >= c0min, h1 = c1max >= c1min;
-    if (!h0 && !h1) { tr.node = stack[--tr.sp]; }
-    else {
-        int next = h0 ? ch.x : ch.y;
-        if (h0 && h1) {
-            int far = ch.y;
-            if (c1min < c0min) { far = ch.x; next = ch.y; }
-            if (tr.sp < TRT_STACK_DEPTH) stack[tr.sp++] = far;
-        }
-        tr.node = next;
+    const float4* nd = sc.nodes + 8 * (size_t)tr.node;
+    const float4 lox = __ldg(nd + 0), hix = __ldg(nd + 1), loy = __ldg(nd + 2), hiy = __ldg(nd + 3);
+    const float4 loz = __ldg(nd + 4), hiz = __ldg(nd + 5);
+    const int4 ch = __ldg((const int4*)(nd + 6));
+    if (COUNT) cnt.box_tests += 4;
+    const float INF = __int_as_float(0x7f800000);
+#define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
+    {                                                                                                      \
+        const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
+        const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
+        const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));           \
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
+        KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
     }
+    float k0, k1, k2, k3;
+    int r0 = ch.x, r1 = ch.y, r2 = ch.z, r3 = ch.w;
+    TRT_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, r0, k0)
+    TRT_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, r1, k1)
+    TRT_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, r2, k2)
+    TRT_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, r3, k3)
+#undef TRT_SLAB
+    order2(k0, r0, k1, r1); order2(k2, r2, k3, r3);
+    order2(k0, r0, k2, r2); order2(k1, r1, k3, r3);
+    order2(k1, r1, k2, r2);
+    // k0 <= k1 <= k2 <= k3; misses carry +inf and sort last
+    int sp = tr.sp;
+    if (k3 < INF) stack[sp++] = r3;
+    if (k2 < INF) stack[sp++] = r2;
+    if (k1 < INF) stack[sp++] = r1;
+    if (k0 < INF) { tr.node = r0; tr.sp = sp; }
+    else { tr.node = stack[sp - 1]; tr.sp = sp - 1; }
 }
 
 // One leaf test for a lane with tr.node < 0: the triangle at leaf position ~node.

@@ -25,6 +25,7 @@ struct RenderArgs {
     // work decomposition
     int chunk, n_chunks, tiles_x, tiles_y;
     int min_steps, exit_num, vote;      // BVH-loop policy, see pathtrace.cu
+    int count_tests, wf_blocks, wf_check; // wavefront engine: count box/tri tests; trace CTAs per SM; waves between liveness checks
     long long n_items;
     unsigned long long* item_counter;   // zeroed before launch
     unsigned long long* counters;       // [0] rays [1] box tests [2] triangle tests [3] sphere tests
@@ -36,6 +37,27 @@ struct ResolveArgs {
     const long long* src[TRT_MAX_RESOLVE_SOURCES];
     double *canva, *albedo, *normal;    // [W*H][3]
 };
+
+// Wavefront engine state: one SLOT per in-flight path, SoA in global memory (see wavefront.cu).
+struct WfState {
+    int n_slots;                 // multiple of 256
+    float4* ray_o;               // (origin, bits(src_prim))
+    float4* ray_d;               // (direction of the ray to trace next, bits(src_twin))
+    float4* hit;                 // (t, bits(prim), u, v)  written by the trace kernel
+    float4* path_T;              // (rayColor, cur_index)
+    float4* path_L;              // (incomingLight, bits(meta))   meta = phase | is_alpha<<2 | bounce<<3 | alpha_depth<<16
+    float4* aov_a;               // (albedo AOV, bits(pixel))
+    float4* aov_n;               // (normal AOV, bits(current sample))
+    float4* dnext;               // (bounce direction parked during an AO query, bits(end sample))
+    long long* acc;              // [9][n_slots] sums of the slot's current item
+    unsigned char* rflag;        // 0 no ray, 1 closest-hit query, 2 any-hit query
+    int* live;                   // slots that are not dead yet
+    unsigned long long* cursor;  // work counter of the trace kernel, reset by the shade kernel
+};
+size_t trt_wavefront_bytes(int n_slots);
+void trt_wavefront_carve(void* base, int n_slots, WfState& S);
+// Runs shade/trace waves until every slot is dead.  Returns the number of kernel launches in *launches.
+cudaError_t trt_launch_wavefront(const RenderArgs& A, WfState& S, int n_sms, int* h_live_pinned, int* launches, cudaStream_t stream);
 
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream);
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
@@ -64,12 +86,12 @@ struct BuildOutputs {            // device buffers allocated by the caller with 
     float4* tri;        // 3*n_tris
     float4* tri_uv;     // 2*n_tris
     int*    tri_orig;   // n_tris
-    float4* nodes;      // 4*max(n_tris-1,1)
+    float4* nodes;      // 8*max(n_tris-1,1): 4-wide nodes, 128 B each (at most n_tris-1 of them)
     float4* texels;     // 3*n_materials*tex_w*tex_h
     // filled by the build
     int root;
     float tri_tmin;
-    int max_depth, n_twins;
+    int max_depth, n_twins, n_wide_nodes, wide_depth, binary_depth;
     double sah_cost;
 };
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream);

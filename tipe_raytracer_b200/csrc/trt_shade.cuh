@@ -1,0 +1,141 @@
+// trt_shade.cuh — the per-hit logic of the reference's tracer() (main.c:118-242) and the per-sample
+// set-up of fill_canva (main.c:264-272), shared by both execution engines (the register-resident
+// megakernel of pathtrace.cu and the wavefront engine of wavefront.cu), so that there is exactly one
+// FP32 restatement of the shading semantics.
+#pragma once
+
+#include "trt_isect.cuh"
+#include "trt_kernels.h"
+
+enum { PH_NEW = 0, PH_BOUNCE = 1, PH_AO = 2, PH_DONE = 3 };
+
+struct PathState {
+    float3 o, d;            // current ray (d is NOT normalised after a mirror/diffuse lerp, main.c:165)
+    float3 d_ao;            // pending ambient-occlusion direction
+    float3 T, L;            // rayColor, incomingLight (main.c:120-121)
+    float3 aov_albedo, aov_normal;
+    float  cur_index;       // the refraction stack collapsed to its top n2 (pile.h)
+    int    bounce;          // i of main.c:132
+    int    alpha_depth;
+    int    src_prim, src_twin;
+    bool   is_alpha;
+};
+
+struct PathResult {         // what one finished path adds to its pixel (col_alb_norm, denoiser.h:11-13)
+    float3 L, albedo, normal;
+};
+
+// fill_canva's per-sample set-up (main.c:265-271) + get_ray (camera.h:42-54).
+// A.cam_corner = coin_bas_gauche - origin, formed in FP64 on the host.
+__device__ __forceinline__ void start_path(const RenderArgs& A, int pixel, int px, int py, int sample, PathState& P)
+{
+    const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + sample), 0u, 0u, A.key0, A.key1);
+    const float u = ((float)px + (u01(r.x) - 0.5f)) * A.inv_wm1;
+    const float v = ((float)py + (u01(r.y) - 0.5f)) * A.inv_hm1;
+    const float dx = (u01(r.z) - 0.5f) * A.aperture_x;
+    const float dy = (u01(r.w) - 0.5f) * A.aperture_y;
+    const float3 direction = fma3(A.cam_hor, u, fma3(A.cam_ver, v, A.cam_corner));
+    const float3 dest = fma3(direction, A.focus, A.cam_origin);
+    P.o = f3(A.cam_origin.x + dx, A.cam_origin.y + dy, A.cam_origin.z);
+    P.d = normalize3(dest - P.o);
+    P.T = f3(1, 1, 1); P.L = f3(0, 0, 0);
+    P.aov_albedo = P.aov_normal = f3(0, 0, 0);
+    P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.is_alpha = false;
+    P.src_prim = TRT_NO_PRIM; P.src_twin = -1;
+}
+
+// One completed closest_hit query -> one trip of the bounce loop (main.c:132-239) or the end of an
+// ambient-occlusion query (main.c:94-116).  `phase` is PH_BOUNCE or PH_AO on entry.
+// Returns true when the path has ended (res is then what it contributes); otherwise P holds the
+// next ray (P.o with P.d, or P.d_ao when phase == PH_AO on exit).
+// sph / sph_mat may point to shared or global memory.
+__device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* __restrict__ sph, const float4* __restrict__ sph_mat,
+                                            int pixel, int sample, float hit_t, int hit_prim, float hit_u, float hit_v,
+                                            PathState& P, int& phase, PathResult& res)
+{
+    const DevScene& sc = A.scene;
+    const bool did_hit = hit_prim != TRT_NO_PRIM;
+
+    if (phase == PH_AO) {
+        // ambient_occlusion (main.c:94-116): distance/dst == 1 for a unit direction, so the term is
+        // 1/AO when anything is hit and 0 otherwise.
+        P.T = P.T * (did_hit ? A.inv_ao : 0.0f);
+        res.L = P.L; res.albedo = P.aov_albedo; res.normal = P.aov_normal;
+        if (P.bounce >= A.bounces) return true;
+        phase = PH_BOUNCE;
+        return false;
+    }
+
+    const int i = P.bounce;
+    Material m;
+    float3 n = f3(0, 0, 0), hp = P.o;
+    int twin = -1;
+    if (did_hit) {
+        hp = fma3(P.d, hit_t, P.o);
+        if (hit_prim < sc.n_spheres) {
+            const float4 cr = sph[hit_prim];
+            n = normalize3(hp - xyz(cr));                                    // sphere.h:33 (always outward)
+            m = unpack_material(sph_mat[3 * hit_prim], sph_mat[3 * hit_prim + 1], sph_mat[3 * hit_prim + 2]);
+        } else {
+            const int leaf = hit_prim - sc.n_spheres;
+            const float4 r2 = __ldg(sc.tri + 3 * leaf + 2);
+            n = normalize3(f3(r2.y, r2.z, r2.w));                            // mesh.h:90
+            m = triangle_material(sc, leaf, hit_u, hit_v, twin);
+        }
+    } else {
+        // the reference reads an uninitialised HitInfo here (main.c:135-139); defined as zeros
+        m = unpack_material(make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0));
+    }
+
+    if (i == 0) { P.aov_albedo = m.diffuse; P.aov_normal = n; }                                   // main.c:137-140
+    if (i == P.alpha_depth && P.is_alpha) {                                                       // main.c:142-150
+        P.aov_albedo = (m.emission_strength > 0.0f) ? m.emission : m.diffuse;
+        P.aov_normal = n;
+        P.is_alpha = false;
+    }
+    res.L = P.L; res.albedo = P.aov_albedo; res.normal = P.aov_normal;
+
+    if (!did_hit) return true;                                                                    // main.c:236-238
+    if (i == P.alpha_depth && m.emission_strength > 0.0f) {
+        // light seen directly (main.c:154-160): HSL round trip with unit gains == identity
+        res.L = m.emission; res.albedo = m.emission; res.normal = n;
+        return true;
+    }
+
+    const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + sample), 1u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
+    const float3 d_in = P.d;
+    P.o = hp;                                                                                     // main.c:162
+    P.src_prim = hit_prim; P.src_twin = twin;
+    const float3 diffuse_dir = normalize3(n + unit_sphere(u01(r.x), u01(r.y)));                   // main.c:163
+    const float3 mirror_dir = reflect3(d_in, n);
+    const float3 mixed = lerp3(diffuse_dir, mirror_dir, m.reflection);                            // main.c:165
+    bool shade = true;
+    if (m.alpha <= 0.99f && m.alpha >= 0.0001f) {                                                 // main.c:167-193
+        float3 nn = n;
+        float n1 = P.cur_index, n2 = m.index;                  // entering: (top.n2, m), push
+        const float before = P.cur_index;
+        P.cur_index = m.index;
+        if (dot3(d_in, n) > 0.0f) {                            // leaving: pop, swap
+            nn = -n; n1 = m.index; n2 = before; P.cur_index = before;
+        }
+        const float3 refr = refract3(d_in, nn, n1, n2);
+        const uint4 rc = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + sample), 2u + 2u * (uint32_t)i, 0u, A.key0, A.key1);
+        if (u01(rc.x) > m.alpha) { P.d = refr; shade = false; }
+        else P.d = mixed;
+    }
+    if (m.alpha > 0.99f) { P.is_alpha = false; P.d = mixed; }                                     // main.c:195-198
+    if (shade && m.alpha < 0.0001f) { P.is_alpha = true; P.alpha_depth++; shade = false; }        // main.c:200-206
+    P.bounce = i + 1;
+    if (shade) {
+        const float k = A.use_ao ? A.emit_scale_ao : 1.0f;                                        // 1.5 * AO (main.c:210)
+        P.L = P.L + (m.emission * (m.emission_strength * k)) * P.T;
+        if (P.T.x > 0.5f || P.T.y > 0.5f || P.T.z > 0.5f) P.T = m.diffuse * (P.T * 1.3f);         // main.c:214-216
+        P.T = m.diffuse * P.T;
+        if (A.use_ao) {
+            P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                             // main.c:100-102
+            phase = PH_AO;
+        }
+    }
+    res.L = P.L;
+    return phase != PH_AO && P.bounce >= A.bounces;
+}
