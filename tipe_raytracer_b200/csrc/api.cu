@@ -133,12 +133,13 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     const bool brute = (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, count_tests = (p->flags & TRT_FLAG_COUNT_TESTS) != 0;
     // engine: triangles => wavefront (small high-occupancy query kernel), spheres only => register-resident megakernel
     int engine = knob("TRT_ENGINE", 0);
-    if (engine == 0) engine = (d.scene.n_tris > 0 && !brute && p->nbRebondMax <= 8191) ? 2 : 1;
+    if (engine == 0) engine = 1;    // measured on B200: the megakernel wins on every reference scene; the wavefront engine is opt-in
     if (engine == 2 && (brute || p->nbRebondMax > 8191)) engine = 1;
     const int chunk_max = engine == 2 ? knob("TRT_TUNE_WF_CHUNK", 16) : knob("TRT_TUNE_CHUNK", 32);
-    A.min_steps = knob("TRT_TUNE_MIN_STEPS", engine == 2 ? 4 : 8);
-    A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 16);
+    A.min_steps = knob("TRT_TUNE_MIN_STEPS", 4);
+    A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 20);
     A.vote = knob("TRT_TUNE_VOTE", 0);
+    A.max_hk = knob("TRT_TUNE_MAX_HK", 4);
     A.count_tests = count_tests ? 1 : 0;
     A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
     A.wf_check = knob("TRT_TUNE_WF_CHECK", 8);
@@ -376,6 +377,7 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
         s.quel_mat = d.quel_mat; s.nodes = d.nodes; s.root = bo.root;
         s.texels = d.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
         s.tri_tmin = bo.tri_tmin;
+        s.root_lo = bo.root_lo; s.root_hi = bo.root_hi;
         if (3 * bo.max_depth + 2 > TRT_STACK_DEPTH)
             return fail(ctx, TRT_ERR_INVALID, "BVH depth %d needs a traversal stack of %d entries (limit %d)", bo.max_depth, 3 * bo.max_depth + 2, TRT_STACK_DEPTH);
         if (&d == &ctx->devs[0]) {

@@ -56,15 +56,21 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.src_prim = TRT_NO_PRIM; P.src_twin = -1; P.is_alpha = false;
     Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
     int stack[TRT_STACK_DEPTH];
+    int pend = 0;                           // parked leaf (0 = none), see bvh_trip
 
     unsigned ray_count = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
 
     for (;;) {
+      // ---- A. housekeeping, repeated (up to max_hk passes) while too few lanes have BVH work: lanes whose
+      //         queries need no traversal (e.g. rays that miss the mesh's bounding box) keep retiring paths
+      //         until the warp has gathered enough rays that do ----------------------------------------
+      unsigned live_mask = 0;
+      for (int hk = 0;; hk++) {
         bool new_ray = false;
 
         // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
-        if (tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)) {
+        if (tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)) {
             PathResult res;
             if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res)) {
                 my_acc[0 * PT_THREADS] += to_fixed(res.L.x);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z);
@@ -132,7 +138,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
             }
         }
-        const unsigned live_mask = __ballot_sync(0xffffffffu, phase != PH_DONE);
+        live_mask = __ballot_sync(0xffffffffu, phase != PH_DONE);
         if (live_mask == 0) break;
 
         // ---- A3. start a path: fill_canva's per-sample set-up (main.c:265-271) --------------------
@@ -143,13 +149,20 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             new_ray = true;
         }
 
-        // ---- A4. new rays: sphere scan + traversal set-up -------------------------------------------
-        const bool ao = (phase == PH_AO);
-        const float3 rd = ao ? P.d_ao : P.d;
+        // ---- A4. new rays: sphere scan, scene-box cull, traversal set-up ---------------------------
         if (new_ray) {
-            ray_begin<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, rd, P.src_prim, P.src_twin, ao, tr, stack, cnt);
+            const bool ao_ray = (phase == PH_AO);
+            ray_begin<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, ao_ray ? P.d_ao : P.d, P.src_prim, P.src_twin, ao_ray, tr, stack, cnt);
             ray_count++;
         }
+        if (!HAS_TRIS || BRUTE || hk + 1 >= A.max_hk) break;
+        const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE || pend != 0));
+        const int n_ready = __popc(__ballot_sync(0xffffffffu, phase != PH_DONE && tr.node == TRT_TRAV_DONE && pend == 0));
+        if (n_ready == 0 || n_inside >= ((A.exit_num * __popc(live_mask) + 31) >> 5)) break;
+      }
+      if (live_mask == 0) break;
+      const bool ao = (phase == PH_AO);
+      const float3 rd = ao ? P.d_ao : P.d;
 
         // ---- B. BVH traversal, left early when too few lanes are still inside ------------------------
         if (HAS_TRIS && !BRUTE) {
@@ -158,20 +171,18 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             const int src_leaf = P.src_prim - sc.n_spheres, twin_leaf = P.src_twin;
             const int exit_below = (A.exit_num * __popc(live_mask) + 31) >> 5;
             for (int step = 0;; step++) {
-                const bool inside = tr.node != TRT_TRAV_DONE;
+                const bool inside = tr.node != TRT_TRAV_DONE || pend != 0;
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
                 if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
-                if (MODE == 0) {
-                    // if-if: every trip, each lane does whatever it is at (a node visit or a leaf test)
+                if (MODE == 1) {
+                    bvh_trip<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, inside, tr, pend, stack, cnt);
+                } else {
+                    // if-if: every trip, each lane does whatever it is at (measured faster than deferral on B200)
                     if (inside) {
                         if (tr.node >= 0) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
                         else bvh_leaf<COUNT>(sc, P.o, rd, src_leaf, twin_leaf, ao, tr, stack, cnt);
                     }
-                } else {
-                    // while-while: descend until this lane holds a leaf (or is done), then all leaves together
-                    while (tr.node >= 0 && tr.node != TRT_TRAV_DONE) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
-                    if (tr.node < 0) bvh_leaf<COUNT>(sc, P.o, rd, src_leaf, twin_leaf, ao, tr, stack, cnt);
                 }
             }
         }

@@ -32,9 +32,11 @@ struct DevScene {
     const double* tri64;        // raw copy of the caller's triangle array (200 B each), caller order
     const int*    quel_mat;     // [n]   caller order
     // 4-wide BVH, 128-byte nodes (one L1 line): lo.x[4] hi.x[4] lo.y[4] hi.y[4] lo.z[4] hi.z[4] child[4] pad
-    // child reference: >= 0 wide node, < 0 leaf ~(leaf position), TRT_CHILD_EMPTY unused slot
+    // child reference: >= 0 wide node, < 0 leaf ~(leaf position), TRT_CHILD_EMPTY unused slot;
+    // the four 32-byte fields {x, y, z, children} of node i sit at slot (field + i) & 3 (L1 bank spreading)
     const float4* nodes;
     int root;                   // 0, or ~0 when there is a single triangle
+    float3 root_lo, root_hi;    // bounds of all triangles (rays that miss them never enter the traversal loop)
     // textures: nbMaterials slabs of tex_h*tex_w texels, 3 float4 per texel, overrides baked in
     const float4* texels;
     int tex_w, tex_h, n_materials;
@@ -99,6 +101,16 @@ __device__ __forceinline__ long long to_fixed(float v)
 {
     v = (v != v) ? 0.0f : fminf(fmaxf(v, -TRT_SAMPLE_CLAMP), TRT_SAMPLE_CLAMP);
     return __float2ll_rn(v * TRT_ACCUM_SCALE);
+}
+
+// 256-bit read-only load (sm_100a: LDG.E.256.CONSTANT).  A divergent gather is bound by L1 wavefronts, one per
+// lane per load instruction: fetching a 128-byte node with four 256-bit loads instead of eight 128-bit ones
+// doubles the node rate (tools/microbench/gather.cu: 36 -> 72 G records/s on B200).  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
+{
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
 }
 
 __device__ __forceinline__ unsigned lanemask_lt()

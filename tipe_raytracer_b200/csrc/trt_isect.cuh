@@ -120,6 +120,18 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
         }
         return;
     }
+    // scene-box cull: a ray that misses the bounds of all triangles (or reaches them beyond the best
+    // sphere hit) never enters the traversal loop
+    {
+        const float3 idir = safe_inverse(d);
+        const float ax = (sc.root_lo.x - o.x) * idir.x, bx = (sc.root_hi.x - o.x) * idir.x;
+        const float ay = (sc.root_lo.y - o.y) * idir.y, by = (sc.root_hi.y - o.y) * idir.y;
+        const float az = (sc.root_lo.z - o.z) * idir.z, bz = (sc.root_hi.z - o.z) * idir.z;
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));
+        if (COUNT) cnt.box_tests += 1;
+        if (!(tf >= tn)) return;
+    }
     stack[0] = TRT_TRAV_DONE;
     tr.sp = 1;
     tr.node = sc.root;
@@ -140,9 +152,11 @@ template <bool COUNT>
 __device__ __forceinline__ void bvh_visit(const DevScene& sc, float3 idir, float3 ood, Trav& tr, int* stack, TraceCounters& cnt)
 {
     const float4* nd = sc.nodes + 8 * (size_t)tr.node;
-    const float4 lox = __ldg(nd + 0), hix = __ldg(nd + 1), loy = __ldg(nd + 2), hiy = __ldg(nd + 3);
-    const float4 loz = __ldg(nd + 4), hiz = __ldg(nd + 5);
-    const int4 ch = __ldg((const int4*)(nd + 6));
+    float4 lox, hix, loy, hiy, loz, hiz, chf, pad;
+    const int rot = tr.node & 3;                    // fields are stored rotated by the node index (bvh_build.cu)
+    ldg256(nd + 2 * ((0 + rot) & 3), lox, hix); ldg256(nd + 2 * ((1 + rot) & 3), loy, hiy);
+    ldg256(nd + 2 * ((2 + rot) & 3), loz, hiz); ldg256(nd + 2 * ((3 + rot) & 3), chf, pad);
+    const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
     if (COUNT) cnt.box_tests += 4;
     const float INF = __int_as_float(0x7f800000);
 #define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
@@ -195,6 +209,44 @@ __device__ __forceinline__ void bvh_leaf(const DevScene& sc, float3 o, float3 d,
         }
     }
     tr.node = next;
+}
+
+// One traversal trip with DEFERRED leaves (speculative traversal, Aila & Laine 2009): a lane that reaches a
+// leaf parks it in `pend` and keeps descending; the triangle tests are executed for the whole warp only when
+// some lane cannot continue (it holds a parked leaf and found another, or ran out of nodes).  Leaf code then
+// runs with many lanes active instead of the 3-5 that happen to be at a leaf in any given trip.  The result is
+// unchanged: every leaf whose box the ray enters is still tested, and ties are broken by primitive index.
+// Must be called by all 32 lanes; `inside` = this lane still has work (node or parked leaf).
+template <bool COUNT>
+__device__ __forceinline__ void bvh_trip(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
+                                         int src_leaf, int twin_leaf, bool any_hit, bool inside,
+                                         Trav& tr, int& pend, int* stack, TraceCounters& cnt)
+{
+    if (inside) {
+        if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
+        if (tr.node < 0 && pend == 0) { pend = tr.node; tr.node = stack[--tr.sp]; }
+    }
+    const bool stuck = inside && pend != 0 && (tr.node < 0 || tr.node == TRT_TRAV_DONE);
+    if (__any_sync(0xffffffffu, stuck)) {
+        if (inside && pend != 0) {
+            const int p = ~pend;
+            pend = 0;
+            if (p != src_leaf && p != twin_leaf) {
+                float t, u, v;
+                const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+                if (COUNT) cnt.tri_tests++;
+                if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
+                    const int ns = sc.n_spheres;
+                    bool take = t < tr.t;
+                    if (t == tr.t && tr.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (tr.prim - ns));
+                    if (take) {
+                        tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
+                        if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; }
+                    }
+                }
+            }
+        }
+    }
 }
 
 // ---- material at the hit ----------------------------------------------------------------------

@@ -24,7 +24,8 @@ struct RenderArgs {
     uint32_t key0, key1;
     // work decomposition
     int chunk, n_chunks, tiles_x, tiles_y;
-    int min_steps, exit_num, vote;      // BVH-loop policy, see pathtrace.cu
+    int min_steps, exit_num, vote;      // BVH-loop policy, see pathtrace.cu (vote = 1: deferred leaves, bvh_trip)
+    int max_hk;                         // megakernel: housekeeping passes per trip
     int count_tests, wf_blocks, wf_check; // wavefront engine: count box/tri tests; trace CTAs per SM; waves between liveness checks
     long long n_items;
     unsigned long long* item_counter;   // zeroed before launch
@@ -91,6 +92,7 @@ struct BuildOutputs {            // device buffers allocated by the caller with 
     // filled by the build
     int root;
     float tri_tmin;
+    float3 root_lo, root_hi;   // padded bounds of all triangles
     int max_depth, n_twins, n_wide_nodes, wide_depth, binary_depth;
     double sah_cost;
 };
