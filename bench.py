@@ -189,7 +189,8 @@ def main():
     r.scene_set(sc)
     W, H = sc.width, sc.height
     npix = W * H
-    rp = S.params_for(sc, spp=spp, sample_offset=rank * spp, sample_total=world * spp)
+    from tipe_raytracer_b200 import distributed as D
+    rp = D.rank_params(S.params_for(sc, spp=spp), rank, world, weak=True)      # rank r: global samples [r*spp, (r+1)*spp)
     ext = torch.cuda.ExternalStream(r.stream_ptr(), device=dev)
     accum = torch.zeros(9 * npix, dtype=torch.int64, device=dev)
     out_dev = torch.zeros(9 * npix, dtype=torch.float64, device=dev)
@@ -207,7 +208,7 @@ def main():
         st = r.accumulate(rp, accum.data_ptr())
         if world > 1:
             with torch.cuda.stream(ext):
-                dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+                D.reduce_accum(accum, dst=0)                       # int64 SUM over NVLink (NCCL)
             if rank == 0:
                 r.resolve_device(rp, accum.data_ptr(), out_dev.data_ptr(), out_dev.data_ptr() + 24 * npix, out_dev.data_ptr() + 48 * npix)
         return st
@@ -256,7 +257,7 @@ def main():
             accum.zero_()
         st = r.accumulate(rp, accum.data_ptr())
         with torch.cuda.stream(ext):
-            dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
+            D.reduce_accum(accum, dst=0)
         if rank == 0:
             res = r.resolve(rp, accum.data_ptr())
             host.update(res)
@@ -290,7 +291,7 @@ def main():
         achieved = rays_per_launch * f_ray / (kernel_ms * 1e-3) / 1e12
         hbm_alg = 9 * 8 * npix * ((spp + 31) // 32)                 # int64 RED traffic of the flushes, per launch
         roofline = {
-            "bound": "fp32", "kernel": "pathtrace_kernel<HAS_TRIS,BVH>", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+            "bound": "fp32", "kernel": "pathtrace_kernel (persistent megakernel, 4-wide BVH)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": achieved / fp32_peak, "traffic": None,
             "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_clock/1e6:.0f} MHz (sm_max_mhz from MEASURED_PEAKS.json, {peak_src})",
             "flops_per_ray": f_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri, "sphere_tests_per_ray": n_sph,
@@ -313,7 +314,7 @@ def main():
             "rays_per_step": rays_total / steps, "rays_per_path": rays_local / steps / (npix * spp),
             "nominal_mrays_s": npix * spp * world * sc.bounces / (ms_per_step * 1e-3) / 1e6,
             "msamples_s": npix * spp * world / (ms_per_step * 1e-3) / 1e6,
-            "clocks": clocks, "gpu_launches": steps * (1 + (1 if world > 1 else 0)),
+            "clocks": clocks, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + (steps if world > 1 else 0),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te_ms / e2e_steps, "steps": e2e_steps, "wall_s": e2e_wall,
                     "what": "trt_scene_set (upload + GPU BVH build) + trt_render into host color arrays"},
