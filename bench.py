@@ -249,8 +249,12 @@ def main():
     h2d = int(sc.spheres.nbytes + sc.triangles.nbytes + sc.mat_list.nbytes + sc.quel_mat_pour_tri.nbytes)
     d2h = 3 * npix * 24
 
+    e2e_parts = {"scene_set_ms": 0.0, "render_ms": 0.0}
+
     def step_e2e():
+        t0 = time.perf_counter()
         r.scene_set(sc)                                   # H2D of the reference-layout arrays + BVH build
+        e2e_parts["scene_set_ms"] += (time.perf_counter() - t0) * 1e3
         if world == 1:
             return r.render(S.params_for(sc, spp=spp), out=host)["stats"]      # trace + resolve + D2H
         with torch.cuda.stream(ext):
@@ -264,6 +268,7 @@ def main():
         return st
 
     step_e2e()
+    e2e_parts = {"scene_set_ms": 0.0, "render_ms": 0.0}
     e2e_steps = max(2, min(steps, 3))
     t0 = time.perf_counter()
     te_ms, est = timed(step_e2e, e2e_steps)
@@ -317,6 +322,7 @@ def main():
             "clocks": clocks, "gpu_launches": int(sum(s["kernel_launches"] for s in stats)) + (steps if world > 1 else 0),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te_ms / e2e_steps, "steps": e2e_steps, "wall_s": e2e_wall,
+                    "scene_set_ms_per_step": e2e_parts["scene_set_ms"] / e2e_steps,
                     "what": "trt_scene_set (upload + GPU BVH build) + trt_render into host color arrays"},
             "roofline": roofline, "bvh": r.bvh_info(),
         }

@@ -18,15 +18,28 @@ namespace {
 
 thread_local std::string g_init_error;
 
+struct Buf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes)
+    {
+        if (bytes == 0) bytes = 256;
+        if (cap >= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes + bytes / 8);      // a little headroom for slightly larger scenes
+        if (e == cudaSuccess) cap = bytes + bytes / 8;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 struct DeviceCtx {
     int dev = 0;
     int n_sms = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
-    // scene
-    double* sph_raw = nullptr; double* tri_raw = nullptr; int* quel_mat = nullptr;
-    float4 *sph = nullptr, *sph_mat = nullptr, *tri = nullptr, *tri_uv = nullptr, *nodes = nullptr, *texels = nullptr;
-    int* tri_orig = nullptr;
+    // scene: grow-only device buffers, reused by every trt_scene_set (no cudaMalloc/cudaFree churn per frame)
+    Buf sph_raw, tri_raw, quel_mat, sph, sph_mat, tri, tri_uv, tri_orig, nodes, texels, mats_raw, ov_raw, scratch;
     DevScene scene{};
     // work buffers
     unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
@@ -67,10 +80,8 @@ int fail(trt_ctx* ctx, int code, const char* fmt, ...)
 void free_scene(DeviceCtx& d)
 {
     cudaSetDevice(d.dev);
-    void* ptrs[] = {d.sph_raw, d.tri_raw, d.quel_mat, d.sph, d.sph_mat, d.tri, d.tri_uv, d.nodes, d.texels, d.tri_orig};
-    for (void* p : ptrs) if (p) cudaFree(p);
-    d.sph_raw = d.tri_raw = nullptr; d.quel_mat = nullptr;
-    d.sph = d.sph_mat = d.tri = d.tri_uv = d.nodes = d.texels = nullptr; d.tri_orig = nullptr;
+    Buf* bufs[] = {&d.sph_raw, &d.tri_raw, &d.quel_mat, &d.sph, &d.sph_mat, &d.tri, &d.tri_uv, &d.tri_orig, &d.nodes, &d.texels, &d.mats_raw, &d.ov_raw, &d.scratch};
+    for (Buf* b : bufs) b->release();
     d.scene = DevScene{};
 }
 
@@ -333,49 +344,44 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
     for (auto& d : ctx->devs) {
         CU(ctx, cudaSetDevice(d.dev));
         CU(ctx, cudaStreamSynchronize(d.stream));
-        free_scene(d);
-        double *mats_raw = nullptr, *ov_raw = nullptr;
         const size_t ns = (size_t)(nbSpheres > 0 ? nbSpheres : 1), nt = (size_t)(nbTriangles > 0 ? nbTriangles : 1);
-        CU(ctx, cudaMalloc(&d.sph_raw, sizeof(trt_sphere) * ns));
-        CU(ctx, cudaMalloc(&d.sph, sizeof(float4) * ns));
-        CU(ctx, cudaMalloc(&d.sph_mat, sizeof(float4) * 3 * ns));
-        CU(ctx, cudaMalloc(&d.tri_raw, sizeof(trt_triangle) * nt));
-        CU(ctx, cudaMalloc(&d.quel_mat, sizeof(int) * nt));
-        CU(ctx, cudaMalloc(&d.tri, sizeof(float4) * 3 * nt));
-        CU(ctx, cudaMalloc(&d.tri_uv, sizeof(float4) * 2 * nt));
-        CU(ctx, cudaMalloc(&d.tri_orig, sizeof(int) * nt));
-        CU(ctx, cudaMalloc(&d.nodes, sizeof(float4) * 8 * nt));
-        CU(ctx, cudaMalloc(&d.texels, sizeof(float4) * 3 * (n_texels > 0 ? n_texels : 1)));
-        if (nbSpheres) CU(ctx, cudaMemcpyAsync(d.sph_raw, sphere_list, sizeof(trt_sphere) * nbSpheres, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, d.sph_raw.ensure(sizeof(trt_sphere) * ns));
+        CU(ctx, d.sph.ensure(sizeof(float4) * ns));
+        CU(ctx, d.sph_mat.ensure(sizeof(float4) * 3 * ns));
+        CU(ctx, d.tri_raw.ensure(sizeof(trt_triangle) * nt));
+        CU(ctx, d.quel_mat.ensure(sizeof(int) * nt));
+        CU(ctx, d.tri.ensure(sizeof(float4) * 3 * nt));
+        CU(ctx, d.tri_uv.ensure(sizeof(float4) * 2 * nt));
+        CU(ctx, d.tri_orig.ensure(sizeof(int) * nt));
+        CU(ctx, d.nodes.ensure(sizeof(float4) * 8 * nt));
+        CU(ctx, d.texels.ensure(sizeof(float4) * 3 * (n_texels > 0 ? n_texels : 1)));
+        CU(ctx, d.scratch.ensure(trt_build_scratch_bytes(nbTriangles)));
+        if (nbSpheres) CU(ctx, cudaMemcpyAsync(d.sph_raw.p, sphere_list, sizeof(trt_sphere) * nbSpheres, cudaMemcpyHostToDevice, d.stream));
         if (nbTriangles) {
-            CU(ctx, cudaMemcpyAsync(d.tri_raw, triangle_list, sizeof(trt_triangle) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
-            CU(ctx, cudaMemcpyAsync(d.quel_mat, quelMatPourTri, sizeof(int) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
-            CU(ctx, cudaMalloc(&mats_raw, sizeof(trt_material) * n_texels));
-            cudaError_t e = cudaMemcpyAsync(mats_raw, mat_list, sizeof(trt_material) * n_texels, cudaMemcpyHostToDevice, d.stream);
-            if (e == cudaSuccess && n_overrides > 0) {
-                e = cudaMalloc(&ov_raw, sizeof(trt_mat_override) * n_overrides);
-                if (e == cudaSuccess) e = cudaMemcpyAsync(ov_raw, overrides, sizeof(trt_mat_override) * n_overrides, cudaMemcpyHostToDevice, d.stream);
-            }
-            if (e != cudaSuccess) { cudaFree(mats_raw); if (ov_raw) cudaFree(ov_raw); CU(ctx, e); }
+            CU(ctx, d.mats_raw.ensure(sizeof(trt_material) * n_texels));
+            CU(ctx, d.ov_raw.ensure(sizeof(trt_mat_override) * (size_t)(n_overrides > 0 ? n_overrides : 1)));
+            CU(ctx, cudaMemcpyAsync(d.tri_raw.p, triangle_list, sizeof(trt_triangle) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaMemcpyAsync(d.quel_mat.p, quelMatPourTri, sizeof(int) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaMemcpyAsync(d.mats_raw.p, mat_list, sizeof(trt_material) * n_texels, cudaMemcpyHostToDevice, d.stream));
+            if (n_overrides > 0) CU(ctx, cudaMemcpyAsync(d.ov_raw.p, overrides, sizeof(trt_mat_override) * n_overrides, cudaMemcpyHostToDevice, d.stream));
         }
         BuildInputs in{};
-        in.spheres_raw = d.sph_raw; in.n_spheres = nbSpheres;
-        in.tris_raw = d.tri_raw; in.n_tris = nbTriangles;
-        in.mats_raw = mats_raw; in.tex_w = tex_width; in.tex_h = tex_height; in.n_materials = nbMaterials;
-        in.quel_mat = d.quel_mat; in.overrides_raw = ov_raw; in.n_overrides = nbTriangles ? n_overrides : 0;
+        in.spheres_raw = (const double*)d.sph_raw.p; in.n_spheres = nbSpheres;
+        in.tris_raw = (const double*)d.tri_raw.p; in.n_tris = nbTriangles;
+        in.mats_raw = (const double*)d.mats_raw.p; in.tex_w = tex_width; in.tex_h = tex_height; in.n_materials = nbMaterials;
+        in.quel_mat = (const int*)d.quel_mat.p; in.overrides_raw = (const double*)d.ov_raw.p; in.n_overrides = nbTriangles ? n_overrides : 0;
+        in.scratch = d.scratch.p; in.scratch_bytes = d.scratch.cap;
         BuildOutputs bo{};
-        bo.sph = d.sph; bo.sph_mat = d.sph_mat; bo.tri = d.tri; bo.tri_uv = d.tri_uv; bo.tri_orig = d.tri_orig;
-        bo.nodes = d.nodes; bo.texels = d.texels;
-        cudaError_t e = trt_build_scene(in, bo, d.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
-        if (mats_raw) cudaFree(mats_raw);
-        if (ov_raw) cudaFree(ov_raw);
-        CU(ctx, e);
+        bo.sph = (float4*)d.sph.p; bo.sph_mat = (float4*)d.sph_mat.p; bo.tri = (float4*)d.tri.p; bo.tri_uv = (float4*)d.tri_uv.p;
+        bo.tri_orig = (int*)d.tri_orig.p; bo.nodes = (float4*)d.nodes.p; bo.texels = (float4*)d.texels.p;
+        CU(ctx, trt_build_scene(in, bo, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        if (d.mats_raw.cap > ((size_t)256 << 20)) d.mats_raw.release();      // big FP64 texture slabs are not kept around
         DevScene& s = d.scene;
-        s.n_spheres = nbSpheres; s.sph = d.sph; s.sph_mat = d.sph_mat; s.sph64 = d.sph_raw;
-        s.n_tris = nbTriangles; s.tri = d.tri; s.tri_uv = d.tri_uv; s.tri_orig = d.tri_orig; s.tri64 = d.tri_raw;
-        s.quel_mat = d.quel_mat; s.nodes = d.nodes; s.root = bo.root;
-        s.texels = d.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
+        s.n_spheres = nbSpheres; s.sph = bo.sph; s.sph_mat = bo.sph_mat; s.sph64 = (const double*)d.sph_raw.p;
+        s.n_tris = nbTriangles; s.tri = bo.tri; s.tri_uv = bo.tri_uv; s.tri_orig = bo.tri_orig; s.tri64 = (const double*)d.tri_raw.p;
+        s.quel_mat = (const int*)d.quel_mat.p; s.nodes = bo.nodes; s.root = bo.root;
+        s.texels = bo.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
         s.tri_tmin = bo.tri_tmin;
         s.root_lo = bo.root_lo; s.root_hi = bo.root_hi;
         if (3 * bo.max_depth + 2 > TRT_STACK_DEPTH)

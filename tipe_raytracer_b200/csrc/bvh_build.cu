@@ -314,16 +314,20 @@ __global__ void collapse_level(const int2* __restrict__ children, const float4* 
     f3[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-struct Scratch {
-    void* ptr = nullptr;
-    ~Scratch() { if (ptr) cudaFree(ptr); }
-};
-
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
 #define BT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
+size_t trt_build_scratch_bytes(int n_tris)
+{
+    if (n_tris <= 0) return 256;
+    size_t cub_bytes = 0;
+    cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n_tris, 0, 64, 0);
+    const size_t n = (size_t)n_tris;
+    return 6 * align256(sizeof(float4) * n) + 2 * align256(8 * n) + 3 * align256(sizeof(int2) * n) + 3 * align256(sizeof(int) * n) + 256 + align256(cub_bytes) + 4096;
+}
 
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream)
 {
@@ -347,7 +351,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     if (n == 0) return cudaSuccess;
     if (n > (1 << IDX_BITS)) return cudaErrorInvalidValue;
 
-    // ---- scratch layout ---------------------------------------------------------------------
+    // ---- scratch layout (the caller owns the buffer: trt_build_scratch_bytes) ------------------------
     size_t cub_bytes = 0;
     BT(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, stream));
     size_t off = 0;
@@ -359,11 +363,10 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     const size_t o_children = take(sizeof(int2) * n), o_parent_node = take(sizeof(int) * n), o_parent_leaf = take(sizeof(int) * n);
     const size_t o_flags = take(sizeof(int) * n);
     const size_t o_queue_a = take(sizeof(int2) * n), o_queue_b = take(sizeof(int2) * n);
-    const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64)
+    const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64), collapse counters
     const size_t o_cub = take(cub_bytes);
-    Scratch scratch;
-    BT(cudaMalloc(&scratch.ptr, off));
-    char* base = (char*)scratch.ptr;
+    if (!in.scratch || in.scratch_bytes < off) return cudaErrorInvalidValue;
+    char* base = (char*)in.scratch;
     float4 *box_lo = (float4*)(base + o_box_lo), *box_hi = (float4*)(base + o_box_hi);
     float4 *leaf_lo = (float4*)(base + o_leaf_lo), *leaf_hi = (float4*)(base + o_leaf_hi);
     float4 *node_lo = (float4*)(base + o_node_lo), *node_hi = (float4*)(base + o_node_hi);

@@ -80,6 +80,7 @@ struct BuildInputs {
     const double* mats_raw;      int tex_w, tex_h, n_materials;   // 10 doubles per texel
     const int*    quel_mat;                         // [n_tris]
     const double* overrides_raw; int n_overrides;   // trt_mat_override, 8 doubles each (first = ordinal|mask)
+    void* scratch; size_t scratch_bytes;            // device scratch of at least trt_build_scratch_bytes(n_tris)
 };
 struct BuildOutputs {            // device buffers allocated by the caller with these element counts
     float4* sph;        // n_spheres
@@ -97,6 +98,7 @@ struct BuildOutputs {            // device buffers allocated by the caller with 
     double sah_cost;
 };
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream);
+size_t trt_build_scratch_bytes(int n_tris);
 
 // Known-answer kernels (leaf functions of K2 run over arrays).
 cudaError_t trt_kat_launch_sphere(int n, const float4* cr, const float* ray, int* hit, float* dst, float* point, float* normal, cudaStream_t s);
