@@ -350,7 +350,7 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
         CU(ctx, d.sph_mat.ensure(sizeof(float4) * 3 * ns));
         CU(ctx, d.tri_raw.ensure(sizeof(trt_triangle) * nt));
         CU(ctx, d.quel_mat.ensure(sizeof(int) * nt));
-        CU(ctx, d.tri.ensure(sizeof(float4) * 3 * nt));
+        CU(ctx, d.tri.ensure(sizeof(float4) * 4 * nt + 256));
         CU(ctx, d.tri_uv.ensure(sizeof(float4) * 2 * nt));
         CU(ctx, d.tri_orig.ensure(sizeof(int) * nt));
         CU(ctx, d.nodes.ensure(sizeof(float4) * 8 * nt));

@@ -8,7 +8,7 @@
 //   1. tri_bounds      per-triangle FP32 box (rounded outward) + centroid; scene bounds by atomics
 //   2. morton_keys     36-bit Morton code of the centroid << 28 | triangle index  (unique 64-bit keys)
 //   3. radix sort      cub::DeviceRadixSort (library; the build is not on the per-ray path)
-//   4. emit_leaves     triangles re-laid out in sorted (leaf) order: A, AB, AC, N as 3 float4 (48 B)
+//   4. emit_leaves     triangles re-laid out in sorted (leaf) order: A, AB, AC, N + ids as 4 float4 (64 B)
 //   5. find_twins      coincident opposite-facing triangles ("doubleface" meshes) share a Morton code and
 //                      are neighbours after the sort; each records the other's leaf position
 //   6. build_hierarchy Karras 2012: one thread per internal node, longest-common-prefix ranges
@@ -139,9 +139,10 @@ __global__ void emit_leaves(int n, const unsigned long long* __restrict__ keys, 
     const double* t = raw + 25 * (size_t)k;
     const double ab[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, ac[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
     const double nx = ab[1] * ac[2] - ab[2] * ac[1], ny = ab[2] * ac[0] - ab[0] * ac[2], nz = ab[0] * ac[1] - ab[1] * ac[0];
-    tri[3 * p + 0] = make_float4((float)t[0], (float)t[1], (float)t[2], (float)ab[0]);
-    tri[3 * p + 1] = make_float4((float)ab[1], (float)ab[2], (float)ac[0], (float)ac[1]);
-    tri[3 * p + 2] = make_float4((float)ac[2], (float)nx, (float)ny, (float)nz);
+    tri[4 * p + 0] = make_float4((float)t[0], (float)t[1], (float)t[2], (float)ab[0]);
+    tri[4 * p + 1] = make_float4((float)ab[1], (float)ab[2], (float)ac[0], (float)ac[1]);
+    tri[4 * p + 2] = make_float4((float)ac[2], (float)nx, (float)ny, (float)nz);
+    tri[4 * p + 3] = make_float4(__int_as_float(k), __int_as_float(-1), __int_as_float(quel_mat[k]), 0.0f);   // caller index, twin, ordinal
     tri_uv[2 * p + 0] = make_float4((float)t[19], (float)t[20], (float)t[21], (float)t[22]);
     tri_uv[2 * p + 1] = make_float4((float)t[23], (float)t[24], __int_as_float(quel_mat[k]), __int_as_float(-1));
     tri_orig[p] = k;
@@ -156,7 +157,7 @@ __device__ __forceinline__ bool same_point(const double* a, const double* b) { r
 // triangle S from its own surface meets the twin at distance 0 < 1e-7 and the reference rejects it
 // (mesh.h:88); in FP32 that distance is noise, so the twin is skipped by id like S itself.
 __global__ void find_twins(int n, const unsigned long long* __restrict__ keys, const double* __restrict__ raw,
-                           float4* tri_uv, int* n_twins)
+                           float4* tri_uv, float4* tri, int* n_twins)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
@@ -177,6 +178,7 @@ __global__ void find_twins(int n, const unsigned long long* __restrict__ keys, c
     }
     if (twin >= 0) {
         tri_uv[2 * p + 1].w = __int_as_float(twin);
+        tri[4 * p + 3].y = __int_as_float(twin);
         atomicAdd(n_twins, 1);
     }
 }
@@ -403,7 +405,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
 
     emit_leaves<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, in.quel_mat, box_lo, box_hi, pad,
                                           out.tri, out.tri_uv, out.tri_orig, leaf_lo, leaf_hi);
-    find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, small + 9);
+    find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, out.tri, small + 9);
     BT(cudaGetLastError());
     if (n == 1) {
         out.root = ~0; out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;

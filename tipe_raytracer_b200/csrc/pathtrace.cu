@@ -179,10 +179,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                     bvh_trip<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, inside, tr, pend, stack, cnt);
                 } else {
                     // if-if: every trip, each lane does whatever it is at (measured faster than deferral on B200)
-                    if (inside) {
-                        if (tr.node >= 0) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
-                        else bvh_leaf<COUNT>(sc, P.o, rd, src_leaf, twin_leaf, ao, tr, stack, cnt);
-                    }
+                    if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
                 }
             }
         }

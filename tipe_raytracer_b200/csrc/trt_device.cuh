@@ -26,7 +26,7 @@ struct DevScene {
     const double* sph64;        // [14n] raw copy of the caller's sphere array (112 B each) for the FP64 primary pass
     // triangles, stored in BVH leaf order
     int n_tris;
-    const float4* tri;          // [3n]  (A.xyz, AB.x) (AB.yz, AC.xy) (AC.z, N.xyz), N = AB x AC un-normalised
+    const float4* tri;          // [4n]  64 B: (A.xyz, AB.x) (AB.yz, AC.xy) (AC.z, N.xyz) (caller index, twin leaf, ordinal, -), N = AB x AC un-normalised
     const float4* tri_uv;       // [2n]  (uvA, uvB) (uvC, bits(material ordinal), bits(twin leaf position or -1))
     const int*    tri_orig;     // [n]   leaf position -> index in the caller's triangle array
     const double* tri64;        // raw copy of the caller's triangle array (200 B each), caller order

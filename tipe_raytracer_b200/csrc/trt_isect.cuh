@@ -110,7 +110,7 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
         for (int p = 0; p < sc.n_tris; p++) {
             if (p == src_leaf || p == src_twin) continue;
             float t, u, v;
-            const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+            const float4 r0 = __ldg(sc.tri + 4 * p), r1 = __ldg(sc.tri + 4 * p + 1), r2 = __ldg(sc.tri + 4 * p + 2);
             if (COUNT) cnt.tri_tests++;
             if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
                 bool take = t < tr.t;
@@ -196,7 +196,7 @@ __device__ __forceinline__ void bvh_leaf(const DevScene& sc, float3 o, float3 d,
     int next = stack[--tr.sp];
     if (p != src_leaf && p != twin_leaf) {
         float t, u, v;
-        const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+        const float4 r0 = __ldg(sc.tri + 4 * p), r1 = __ldg(sc.tri + 4 * p + 1), r2 = __ldg(sc.tri + 4 * p + 2);
         if (COUNT) cnt.tri_tests++;
         if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
             const int ns = sc.n_spheres;
@@ -209,6 +209,70 @@ __device__ __forceinline__ void bvh_leaf(const DevScene& sc, float3 o, float3 d,
         }
     }
     tr.node = next;
+}
+
+// One traversal step with a UNIFIED FETCH: whatever the lane is at — a 4-wide node (128 B) or a leaf's triangle
+// (64 B) — its record is requested first, with 256-bit loads, and only then do the two code paths (slab tests /
+// Moller-Trumbore) run.  In the plain if-if loop the leaf path's loads were issued after the node path had
+// finished: two dependent L1/L2 round trips per trip, and 40 % of all stall samples sat on the triangle fetch.
+template <bool COUNT>
+__device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
+                                                 int src_leaf, int twin_leaf, bool any_hit, Trav& tr, int* stack, TraceCounters& cnt)
+{
+    const bool leaf = tr.node < 0;
+    const int idx = leaf ? ~tr.node : tr.node;
+    const float4* rec = leaf ? sc.tri + 4 * (size_t)idx : sc.nodes + 8 * (size_t)idx;
+    const int rot = leaf ? 0 : (idx & 3);
+    float4 f0a, f0b, f1a, f1b, f2a = make_float4(0, 0, 0, 0), f2b = f2a, f3a = f2a, f3b = f2a;
+    ldg256(rec + 2 * ((0 + rot) & 3), f0a, f0b);
+    ldg256(rec + 2 * ((1 + rot) & 3), f1a, f1b);
+    if (!leaf) {
+        ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b);
+        ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
+        if (COUNT) cnt.box_tests += 4;
+        const float INF = __int_as_float(0x7f800000);
+#define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
+    {                                                                                                      \
+        const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
+        const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
+        const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));           \
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
+        KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
+    }
+        float k0, k1, k2, k3;
+        int r0 = __float_as_int(f3a.x), r1 = __float_as_int(f3a.y), r2 = __float_as_int(f3a.z), r3 = __float_as_int(f3a.w);
+        TRT_SLAB(f0a.x, f0b.x, f1a.x, f1b.x, f2a.x, f2b.x, r0, k0)
+        TRT_SLAB(f0a.y, f0b.y, f1a.y, f1b.y, f2a.y, f2b.y, r1, k1)
+        TRT_SLAB(f0a.z, f0b.z, f1a.z, f1b.z, f2a.z, f2b.z, r2, k2)
+        TRT_SLAB(f0a.w, f0b.w, f1a.w, f1b.w, f2a.w, f2b.w, r3, k3)
+#undef TRT_SLAB
+        order2(k0, r0, k1, r1); order2(k2, r2, k3, r3);
+        order2(k0, r0, k2, r2); order2(k1, r1, k3, r3);
+        order2(k1, r1, k2, r2);
+        int sp = tr.sp;
+        if (k3 < INF) stack[sp++] = r3;
+        if (k2 < INF) stack[sp++] = r2;
+        if (k1 < INF) stack[sp++] = r1;
+        if (k0 < INF) { tr.node = r0; tr.sp = sp; }
+        else { tr.node = stack[sp - 1]; tr.sp = sp - 1; }
+    } else {
+        int next = stack[--tr.sp];
+        if (idx != src_leaf && idx != twin_leaf) {
+            float t, u, v;
+            if (COUNT) cnt.tri_tests++;
+            if (triangle_test(f0a, f0b, f1a, o, d, sc.tri_tmin, t, u, v)) {
+                const int ns = sc.n_spheres;
+                bool take = t < tr.t;
+                if (t == tr.t && tr.prim >= ns) take = __float_as_int(f1b.x) < __ldg(sc.tri_orig + (tr.prim - ns));
+                if (take) {
+                    tr.t = t; tr.prim = ns + idx; tr.u = u; tr.v = v;
+                    if (any_hit) next = TRT_TRAV_DONE;
+                }
+            }
+        }
+        tr.node = next;
+    }
 }
 
 // One traversal trip with DEFERRED leaves (speculative traversal, Aila & Laine 2009): a lane that reaches a
@@ -233,7 +297,7 @@ __device__ __forceinline__ void bvh_trip(const DevScene& sc, float3 o, float3 d,
             pend = 0;
             if (p != src_leaf && p != twin_leaf) {
                 float t, u, v;
-                const float4 r0 = __ldg(sc.tri + 3 * p), r1 = __ldg(sc.tri + 3 * p + 1), r2 = __ldg(sc.tri + 3 * p + 2);
+                const float4 r0 = __ldg(sc.tri + 4 * p), r1 = __ldg(sc.tri + 4 * p + 1), r2 = __ldg(sc.tri + 4 * p + 2);
                 if (COUNT) cnt.tri_tests++;
                 if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
                     const int ns = sc.n_spheres;

@@ -85,7 +85,7 @@ struct BuildInputs {
 struct BuildOutputs {            // device buffers allocated by the caller with these element counts
     float4* sph;        // n_spheres
     float4* sph_mat;    // 3*n_spheres
-    float4* tri;        // 3*n_tris
+    float4* tri;        // 4*n_tris (+ slack: the unified fetch may read 64 B past a record)
     float4* tri_uv;     // 2*n_tris
     int*    tri_orig;   // n_tris
     float4* nodes;      // 8*max(n_tris-1,1): 4-wide nodes, 128 B each (at most n_tris-1 of them)

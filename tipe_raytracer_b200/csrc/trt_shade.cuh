@@ -78,7 +78,7 @@ __device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* _
             m = unpack_material(sph_mat[3 * hit_prim], sph_mat[3 * hit_prim + 1], sph_mat[3 * hit_prim + 2]);
         } else {
             const int leaf = hit_prim - sc.n_spheres;
-            const float4 r2 = __ldg(sc.tri + 3 * leaf + 2);
+            const float4 r2 = __ldg(sc.tri + 4 * leaf + 2);
             n = normalize3(f3(r2.y, r2.z, r2.w));                            // mesh.h:90
             m = triangle_material(sc, leaf, hit_u, hit_v, twin);
         }

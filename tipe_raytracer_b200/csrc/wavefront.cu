@@ -232,10 +232,7 @@ wf_trace_kernel(const __grid_constant__ RenderArgs A, const __grid_constant__ Wf
                 if (in_mask == 0) break;
                 if (more && step >= A.min_steps && __popc(in_mask) < A.exit_num) break;
                 if (A.vote) bvh_trip<COUNT>(sc, o, d, idir, ood, src_leaf, src_twin, any_hit, inside, tr, pend, stack, cnt);
-                else if (inside) {
-                    if (tr.node >= 0) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
-                    else bvh_leaf<COUNT>(sc, o, d, src_leaf, src_twin, any_hit, tr, stack, cnt);
-                }
+                else if (inside) bvh_step_unified<COUNT>(sc, o, d, idir, ood, src_leaf, src_twin, any_hit, tr, stack, cnt);
             }
         }
     }
