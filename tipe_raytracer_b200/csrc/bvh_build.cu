@@ -11,13 +11,17 @@
 //   4. emit_leaves     triangles re-laid out in sorted (leaf) order: A, AB, AC, N + ids as 4 float4 (64 B)
 //   5. find_twins      coincident opposite-facing triangles ("doubleface" meshes) share a Morton code and
 //                      are neighbours after the sort; each records the other's leaf position
-//   6. build_hierarchy Karras 2012: one thread per internal node, longest-common-prefix ranges
-//   7. refit           bottom-up boxes, second arriver at each node continues (atomic flags)
+//   6. hierarchy       PLOC (Meister & Bittner 2018), the default: clusters in Morton order repeatedly merge with
+//                      their mutual nearest neighbour (surface area of the union, search radius 16) — close to
+//                      SAH-sweep quality, ~30 small launches.  TRT_BVH=lbvh selects the Karras 2012 LBVH instead
+//                      (one thread per internal node, longest-common-prefix ranges, then a bottom-up refit)
 //   8. sah_cost        surface-area cost of the binary tree (reported through trt_bvh_info)
 //   9. collapse_level  binary -> 4-wide: each surviving node adopts its grandchildren, largest box first,
 //                      until it has 4 children; one launch per level of the wide tree.  128-byte nodes
 //                      (one L1 line): 4 child boxes as 6 float4 (SoA) + int4 child references
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cstdlib>
 
 #include "trt_kernels.h"
 
@@ -250,15 +254,72 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi)
     return dx * dy + dy * dz + dz * dx;
 }
 
+// ---- PLOC ----------------------------------------------------------------------------------------------
+// Clusters live in Morton order in (cid, clo, chi): cid < 0 is leaf ~p, cid >= 0 an internal node.
+__global__ void ploc_nearest(int c, const float4* __restrict__ clo, const float4* __restrict__ chi, int radius, int* nn)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const float4 lo = clo[i], hi = chi[i];
+    float best = 3.0e38f; int bj = -1;
+    const int j0 = max(0, i - radius), j1 = min(c - 1, i + radius);
+    for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const float4 l2 = clo[j], h2 = chi[j];
+        const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+        const float a = dx * dy + dy * dz + dz * dx;
+        if (a < best) { best = a; bj = j; }          // ties: lowest j, so "mutual" is symmetric and deterministic
+    }
+    nn[i] = bj;
+}
+
+// Mutual nearest neighbours merge into a new internal node (owned by the lower index); flag[i] = cluster i survives.
+__global__ void ploc_merge(int c, int* cid, float4* clo, float4* chi, const int* __restrict__ nn, int* node_counter,
+                           int2* children, float4* node_lo, float4* node_hi, int* flag)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const int j = nn[i];
+    int keep = 1;
+    if (j >= 0 && nn[j] == i) {
+        if (i < j) {
+            const int node = atomicAdd(node_counter, 1);
+            const float4 lo = clo[i], hi = chi[i], l2 = clo[j], h2 = chi[j];
+            const float4 mlo = make_float4(fminf(lo.x, l2.x), fminf(lo.y, l2.y), fminf(lo.z, l2.z), 0.0f);
+            const float4 mhi = make_float4(fmaxf(hi.x, h2.x), fmaxf(hi.y, h2.y), fmaxf(hi.z, h2.z), 0.0f);
+            children[node] = make_int2(cid[i], cid[j]);
+            node_lo[node] = mlo; node_hi[node] = mhi;
+            cid[i] = node; clo[i] = mlo; chi[i] = mhi;      // nobody else reads slot i's box in this kernel's remainder: j only checks nn
+        } else keep = 0;
+    }
+    flag[i] = keep;
+}
+
+__global__ void ploc_compact(int c, const int* __restrict__ cid, const float4* __restrict__ clo, const float4* __restrict__ chi,
+                             const int* __restrict__ flag, const int* __restrict__ pos, int* cid2, float4* clo2, float4* chi2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c || !flag[i]) return;
+    const int q = pos[i];
+    cid2[q] = cid[i]; clo2[q] = clo[i]; chi2[q] = chi[i];
+}
+
+__global__ void ploc_init(int n, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int* cid, float4* clo, float4* chi)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    cid[p] = ~p; clo[p] = leaf_lo[p]; chi[p] = leaf_hi[p];
+}
+
 __global__ void sah_cost_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                                const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, double* sah)
+                                const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, int root, double* sah)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     double cost = 0.0;
     if (i < n - 1) {
         const int2 ch = children[i];
         // SAH with C_box = 1 per child box test and C_tri = 1 per leaf, relative to the root area
-        const float root_area = fmaxf(half_area(node_lo[0], node_hi[0]), 1e-30f);
+        const float root_area = fmaxf(half_area(node_lo[root], node_hi[root]), 1e-30f);
         cost = (double)(half_area(node_lo[i], node_hi[i]) / root_area) * 2.0;
         if (ch.x < 0) cost += (double)(half_area(leaf_lo[~ch.x], leaf_hi[~ch.x]) / root_area);
         if (ch.y < 0) cost += (double)(half_area(leaf_lo[~ch.y], leaf_hi[~ch.y]) / root_area);
@@ -325,10 +386,12 @@ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 size_t trt_build_scratch_bytes(int n_tris)
 {
     if (n_tris <= 0) return 256;
-    size_t cub_bytes = 0;
+    size_t cub_bytes = 0, scan_bytes = 0;
     cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n_tris, 0, 64, 0);
+    cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, n_tris, 0);
+    if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
     const size_t n = (size_t)n_tris;
-    return 6 * align256(sizeof(float4) * n) + 2 * align256(8 * n) + 3 * align256(sizeof(int2) * n) + 3 * align256(sizeof(int) * n) + 256 + align256(cub_bytes) + 4096;
+    return 8 * align256(sizeof(float4) * n) + 2 * align256(8 * n) + 3 * align256(sizeof(int2) * n) + 3 * align256(sizeof(int) * n) + 256 + align256(cub_bytes) + 4096;
 }
 
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream)
@@ -354,8 +417,10 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     if (n > (1 << IDX_BITS)) return cudaErrorInvalidValue;
 
     // ---- scratch layout (the caller owns the buffer: trt_build_scratch_bytes) ------------------------
-    size_t cub_bytes = 0;
+    size_t cub_bytes = 0, scan_bytes = 0;
     BT(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, stream));
+    BT(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, n, stream));
+    if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
     const size_t o_box_lo = take(sizeof(float4) * n), o_box_hi = take(sizeof(float4) * n);
@@ -365,7 +430,8 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     const size_t o_children = take(sizeof(int2) * n), o_parent_node = take(sizeof(int) * n), o_parent_leaf = take(sizeof(int) * n);
     const size_t o_flags = take(sizeof(int) * n);
     const size_t o_queue_a = take(sizeof(int2) * n), o_queue_b = take(sizeof(int2) * n);
-    const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64), collapse counters
+    const size_t o_c1lo = take(sizeof(float4) * n), o_c1hi = take(sizeof(float4) * n);     // PLOC ping-pong cluster boxes
+    const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64), collapse counters, PLOC node counter
     const size_t o_cub = take(cub_bytes);
     if (!in.scratch || in.scratch_bytes < off) return cudaErrorInvalidValue;
     char* base = (char*)in.scratch;
@@ -410,14 +476,46 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     if (n == 1) {
         out.root = ~0; out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;
     } else {
-        build_hierarchy<<<grid_n, TB, 0, stream>>>(n, keys_b, children, parent_node, parent_leaf);
-        refit<<<grid_n, TB, 0, stream>>>(n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, small + 8);
-        sah_cost_kernel<<<grid_n, TB, 0, stream>>>(n, children, leaf_lo, leaf_hi, node_lo, node_hi, sah);
+        int root = 0;
+        const char* mode = getenv("TRT_BVH");
+        if (mode && strcmp(mode, "lbvh") == 0) {
+            build_hierarchy<<<grid_n, TB, 0, stream>>>(n, keys_b, children, parent_node, parent_leaf);
+            refit<<<grid_n, TB, 0, stream>>>(n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, small + 8);
+        } else {
+            // PLOC: clusters ping-pong between (queue_a | box_lo | box_hi) and (queue_b | c1lo | c1hi)
+            int* cid[2] = {(int*)(base + o_queue_a), (int*)(base + o_queue_b)};
+            int* nn = cid[0] + n; int* flag = cid[1] + n; int* pos = parent_node;
+            float4* clo[2] = {box_lo, (float4*)(base + o_c1lo)};
+            float4* chi[2] = {box_hi, (float4*)(base + o_c1hi)};
+            int* node_counter = small + 26;
+            const int radius = 16;
+            BT(cudaMemsetAsync(node_counter, 0, sizeof(int), stream));
+            ploc_init<<<grid_n, TB, 0, stream>>>(n, leaf_lo, leaf_hi, cid[0], clo[0], chi[0]);
+            int c = n, cur = 0, h_last[2];
+            for (int iter = 0; c > 1; iter++) {
+                const int g = (c + TB - 1) / TB;
+                ploc_nearest<<<g, TB, 0, stream>>>(c, clo[cur], chi[cur], radius, nn);
+                ploc_merge<<<g, TB, 0, stream>>>(c, cid[cur], clo[cur], chi[cur], nn, node_counter, children, node_lo, node_hi, flag);
+                { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, flag, pos, c, stream)); }
+                ploc_compact<<<g, TB, 0, stream>>>(c, cid[cur], clo[cur], chi[cur], flag, pos, cid[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1]);
+                BT(cudaGetLastError());
+                BT(cudaMemcpyAsync(h_last, pos + c - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                BT(cudaMemcpyAsync(h_last + 1, flag + c - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                BT(cudaStreamSynchronize(stream));
+                const int c_new = h_last[0] + h_last[1];
+                if (c_new >= c || c_new < 1 || iter > 4096) return cudaErrorUnknown;     // every pass merges at least one pair
+                c = c_new; cur ^= 1;
+            }
+            BT(cudaMemcpyAsync(&root, cid[cur], sizeof(int), cudaMemcpyDeviceToHost, stream));
+            BT(cudaStreamSynchronize(stream));
+            if (root < 0 || root >= n - 1) return cudaErrorUnknown;
+        }
+        sah_cost_kernel<<<grid_n, TB, 0, stream>>>(n, children, leaf_lo, leaf_hi, node_lo, node_hi, root, sah);
         BT(cudaGetLastError());
         // binary -> 4-wide, one launch per level (the queue sizes come back to the host: ~depth/2 round trips)
         int2* q[2] = {(int2*)(base + o_queue_a), (int2*)(base + o_queue_b)};
         int* counters = small + 24;
-        const int2 root_entry = make_int2(0, 0);
+        const int2 root_entry = make_int2(root, 0);
         int h_counters[2] = {1, 0};
         BT(cudaMemcpyAsync(q[0], &root_entry, sizeof(int2), cudaMemcpyHostToDevice, stream));
         BT(cudaMemcpyAsync(counters, h_counters, sizeof h_counters, cudaMemcpyHostToDevice, stream));
