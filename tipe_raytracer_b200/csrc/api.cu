@@ -146,15 +146,15 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     int engine = knob("TRT_ENGINE", 0);
     if (engine == 0) engine = 1;    // measured on B200: the megakernel wins on every reference scene; the wavefront engine is opt-in
     if (engine == 2 && (brute || p->nbRebondMax > 8191)) engine = 1;
-    const int chunk_max = engine == 2 ? knob("TRT_TUNE_WF_CHUNK", 16) : knob("TRT_TUNE_CHUNK", 32);
+    const int chunk_max = engine == 2 ? knob("TRT_TUNE_WF_CHUNK", 16) : knob("TRT_TUNE_CHUNK", 16);
     A.min_steps = knob("TRT_TUNE_MIN_STEPS", 4);
-    A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 20);
+    A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 16);
     A.vote = knob("TRT_TUNE_VOTE", 0);
-    A.max_hk = knob("TRT_TUNE_MAX_HK", 4);
+    A.max_hk = knob("TRT_TUNE_MAX_HK", 1);
     A.count_tests = count_tests ? 1 : 0;
     A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
     A.wf_check = knob("TRT_TUNE_WF_CHECK", 8);
-    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (2 with triangles, 3 without)
+    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (3 CTAs of 256 threads per SM, 80 registers)
     A.chunk = spp < chunk_max ? spp : chunk_max;
     A.n_chunks = (spp + A.chunk - 1) / A.chunk;
     A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;

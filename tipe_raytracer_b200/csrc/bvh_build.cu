@@ -12,7 +12,7 @@
 //   5. find_twins      coincident opposite-facing triangles ("doubleface" meshes) share a Morton code and
 //                      are neighbours after the sort; each records the other's leaf position
 //   6. hierarchy       PLOC (Meister & Bittner 2018), the default: clusters in Morton order repeatedly merge with
-//                      their mutual nearest neighbour (surface area of the union, search radius 16) — close to
+//                      their mutual nearest neighbour (surface area of the union, search radius 64) — close to
 //                      SAH-sweep quality, ~30 small launches.  TRT_BVH=lbvh selects the Karras 2012 LBVH instead
 //                      (one thread per internal node, longest-common-prefix ranges, then a bottom-up refit)
 //   8. sah_cost        surface-area cost of the binary tree (reported through trt_bvh_info)
@@ -488,7 +488,8 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
             float4* clo[2] = {box_lo, (float4*)(base + o_c1lo)};
             float4* chi[2] = {box_hi, (float4*)(base + o_c1hi)};
             int* node_counter = small + 26;
-            const int radius = 16;
+            const char* rad = getenv("TRT_TUNE_PLOC_RADIUS");
+            const int radius = rad && *rad ? atoi(rad) : 64;
             BT(cudaMemsetAsync(node_counter, 0, sizeof(int), stream));
             ploc_init<<<grid_n, TB, 0, stream>>>(n, leaf_lo, leaf_hi, cid[0], clo[0], chi[0]);
             int c = n, cur = 0, h_last[2];

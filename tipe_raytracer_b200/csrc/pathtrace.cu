@@ -19,13 +19,16 @@
 #include "trt_shade.cuh"
 
 #define PT_THREADS 256
+#ifndef PT_MIN_BLOCKS
+#define PT_MIN_BLOCKS 3
+#endif
 #define PT_POOL 32
 // Traversal-loop exit policy (RenderArgs.min_steps / exit_num): a warp always takes min_steps BVH steps,
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
 template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE>
-__global__ void __launch_bounds__(PT_THREADS, HAS_TRIS ? 2 : 3)
+__global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
     extern __shared__ float4 smem[];
@@ -243,7 +246,7 @@ static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cu
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream)
 {
     const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4) + sizeof(long long) * 9 * PT_THREADS;
-    const int grid = n_sms * (blocks_per_sm > 0 ? blocks_per_sm : (A.scene.n_tris > 0 ? 2 : 3));
+    const int grid = n_sms * (blocks_per_sm > 0 ? blocks_per_sm : PT_MIN_BLOCKS);
     const bool has_tris = A.scene.n_tris > 0;
     if (!has_tris) return count_tests ? launch_variant<false, false, true>(A, grid, smem, stream)
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
