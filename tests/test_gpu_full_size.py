@@ -1,0 +1,87 @@
+"""BASELINE.json's configurations at FULL size on the GPU, checked through size-independent properties
+(the CPU oracle needs hours for these): exact additivity of sample ranges, engine equivalence, value ranges,
+rays-per-path and image statistics against the oracle at a size it can finish."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.oracle_py import RNG_PHILOX
+from tipe_raytracer_b200 import distributed as D
+from tipe_raytracer_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+
+def _accumulate(rt, rp):
+    n = rp.width * rp.height
+    acc = torch.zeros(9 * n, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    st = rt.accumulate(rp, acc.data_ptr())
+    torch.cuda.synchronize()
+    return acc, st
+
+
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C4"])
+def test_full_size_sample_ranges_add_up_exactly(rt, cfg):
+    sc = S.CONFIGS[cfg]()
+    rt.scene_set(sc)
+    rp = S.params_for(sc)                                   # full resolution, full spp
+    full, st = _accumulate(rt, rp)
+    assert st["paths"] == rp.width * rp.height * rp.spp
+    parts = torch.zeros_like(full)
+    rays = 0
+    for r in range(3):                                       # the 3-GPU split of the same job
+        acc, s = _accumulate(rt, D.rank_params(rp, r, 3))
+        parts += acc
+        rays += s["rays"]
+    assert torch.equal(parts, full) and rays == st["rays"]  # int64 sums: bit-identical, whatever the split
+    res = rt.resolve(rp, full.data_ptr())
+    c = res["canva"]
+    assert c.min() >= 0 and c.max() <= 255 and np.array_equal(c, np.floor(c))
+    assert res["albedo"].min() >= -1e-9 and res["albedo"].max() <= 1.0 + 1e-6
+    assert np.linalg.norm(res["normal"], axis=1).max() <= 1.0 + 1e-5          # mean of unit normals
+    # against the oracle at a size it can finish: same camera, same scene
+    small = S.params_for(sc, width=96, spp=8)
+    o = __import__("oracle.oracle_py", fromlist=["Oracle"]).Oracle().render(sc, small, rng=RNG_PHILOX, want_sums=True)
+    assert abs(st["rays"] / st["paths"] - o["stats"]["rays"] / o["stats"]["paths"]) < 0.05
+    # mean LINEAR radiance (the tonemap's sqrt makes means of noisy images spp-dependent; sums are unbiased)
+    n = rp.width * rp.height
+    lin_gpu = full.view(9, n)[:3].double().mean(dim=1).cpu().numpy() / D.ACCUM_SCALE / rp.spp
+    lin_cpu = o["sums"][:, :3].mean(0) / small.spp
+    assert np.abs(lin_gpu / lin_cpu - 1).max() < 0.05, (lin_gpu, lin_cpu)
+
+
+def test_full_size_c2_engines_agree(rt):
+    sc = S.nature_mesh()
+    rt.scene_set(sc)
+    rp = S.params_for(sc, spp=50)
+    try:
+        os.environ["TRT_ENGINE"] = "1"
+        a, sa = _accumulate(rt, rp)
+        os.environ["TRT_ENGINE"] = "2"
+        b, sb = _accumulate(rt, rp)
+    finally:
+        os.environ.pop("TRT_ENGINE", None)
+    assert torch.equal(a, b) and sa["rays"] == sb["rays"]
+
+
+def test_full_size_c5_readme_benchmark_statistics(rt, oracle):
+    """README benchmark config (1200x900, 1000 spp, 6 bounces, AO): ~11 G rays; checks rays/path and image means
+    against the oracle at 150x112x24 spp (same scene, same estimator, so the means agree up to noise)."""
+    sc = S.readme_benchmark()
+    rt.scene_set(sc)
+    rp = S.params_for(sc)
+    acc, st = _accumulate(rt, rp)
+    assert st["paths"] == 1200 * 900 * 1000
+    res = rt.resolve(rp, acc.data_ptr())
+    small = S.params_for(sc, width=150, spp=24)
+    o = oracle.render(sc, small, rng=RNG_PHILOX, want_sums=True)
+    assert abs(st["rays"] / st["paths"] - o["stats"]["rays"] / o["stats"]["paths"]) < 0.02
+    n = rp.width * rp.height
+    lin_gpu = acc.view(9, n)[:3].double().mean(dim=1).cpu().numpy() / D.ACCUM_SCALE / rp.spp
+    lin_cpu = o["sums"][:, :3].mean(0) / small.spp
+    assert np.abs(lin_gpu / lin_cpu - 1).max() < 0.03, (lin_gpu, lin_cpu)        # unbiased linear means
+    assert np.abs(res["albedo"].mean(0) - o["albedo"].mean(0)).max() < 0.01
+    assert res["canva"].max() <= 255 and res["canva"].min() >= 0
