@@ -10,7 +10,8 @@ __global__ void kat_sphere(int n, const float4* cr, const float* ray, int* hit, 
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float3 o = f3(ray[6 * k], ray[6 * k + 1], ray[6 * k + 2]), d = f3(ray[6 * k + 3], ray[6 * k + 4], ray[6 * k + 5]);
-    const float t = sphere_root(cr[k], o, d, dot3(d, d), false);
+    const float a = dot3(d, d);
+    const float t = sphere_root(cr[k], o, d, a, __frcp_rn(a), false);
     hit[k] = t >= 0.0f;
     dst[k] = t;
     const float3 p = fma3(d, t, o);

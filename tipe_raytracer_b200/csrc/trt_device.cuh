@@ -91,7 +91,7 @@ __device__ __forceinline__ float3 unit_sphere(float u, float v)
     const float z = fmaf(2.0f, v, -1.0f);
     const float s = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
     float sn, cs;
-    sincospif(2.0f * u, &sn, &cs);
+    __sincosf(6.283185307179586f * u, &sn, &cs);       // MUFU.SIN/COS: abs error ~2^-21 over [0, 2*pi), ample for a sampling direction
     return f3(cs * s, sn * s, z);
 }
 

@@ -26,7 +26,7 @@ struct TraceCounters {
 
 // sphere.h:13-47.  Returns the accepted root (near if >= 1e-4, else far if >= 1e-4) or -1.
 // `on_surface`: the ray starts on this very sphere => c = |oc|^2 - r^2 is 0 by construction.
-__device__ __forceinline__ float sphere_root(float4 cr, float3 o, float3 d, float a, bool on_surface)
+__device__ __forceinline__ float sphere_root(float4 cr, float3 o, float3 d, float a, float inv_a, bool on_surface)
 {
     const float3 oc = f3(o.x - cr.x, o.y - cr.y, o.z - cr.z);
     const float hb = dot3(oc, d);                                   // b / 2
@@ -34,9 +34,9 @@ __device__ __forceinline__ float sphere_root(float4 cr, float3 o, float3 d, floa
     if (on_surface) c = 0.0f;
     const float qd = fmaf(hb, hb, -a * c);                          // discriminant / 4
     if (!(qd > 0.0f)) return -1.0f;                                 // sphere.h:27 (strict)
-    const float sq = sqrtf(qd);
+    const float sq = qd * rsqrtf(qd);                               // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL
     const float q = -(hb + copysignf(sq, hb));                      // never cancels
-    const float ra = __fdividef(q, a);
+    const float ra = q * inv_a;
     const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
     const float t1 = fminf(ra, rb), t2 = fmaxf(ra, rb);
     if (t1 >= 1e-4f) return t1;                                     // sphere.h:29
@@ -96,9 +96,10 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
     tr.node = TRT_TRAV_DONE;
     tr.sp = 0;
     const float a = dot3(d, d);
+    const float inv_a = __frcp_rn(a);
     const int ns = sc.n_spheres;
     for (int k = 0; k < ns; k++) {
-        const float t = sphere_root(s_sph[k], o, d, a, k == src_prim);
+        const float t = sphere_root(s_sph[k], o, d, a, inv_a, k == src_prim);
         if (t >= 0.0f && t < tr.t) { tr.t = t; tr.prim = k; }
     }
     if (COUNT) cnt.sphere_tests += ns;
