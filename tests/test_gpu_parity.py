@@ -85,7 +85,7 @@ def test_tonemap_matches_reference_on_fixed_point_sums(rt, golden):
 
 
 # ---- 1. primary-hit buffers ---------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4", "C3b"])
 def test_primary_matches_golden(rt, golden, cfg):
     g = golden["primary"]
     sc = S.CONFIGS[cfg]()
@@ -154,6 +154,13 @@ def test_render_c2_mesh_same_stream(rt, oracle):
 def test_render_c4_tree_same_stream(rt, oracle):
     sc = S.tree_mesh()
     _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+
+
+def test_render_c3b_pyramide_eau_same_stream(rt, oracle):
+    """The scene main.c ships configured for: light / glass / water overrides, 20 bounces, coordinates up to 1800
+    (FP32 ulp there is 1e-4, a thousand times the reference's 1e-7 triangle threshold)."""
+    sc = S.pyramide_eau()
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=128, spp=8), 0.90, 1.5)
 
 
 def test_bvh_equals_linear_scan(rt):

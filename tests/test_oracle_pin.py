@@ -17,7 +17,7 @@ libc = ctypes.CDLL(None)
 
 
 def _scene(name):
-    base = name.split("_")[0]
+    base = name.split("_")[0]          # "C1_noao" -> C1
     sc = S.CONFIGS[base]()
     if name.endswith("_noao"):
         sc.use_ao = False
@@ -122,7 +122,7 @@ def test_philox_known_answers(oracle):
 
 
 # ---- primary-hit buffers ------------------------------------------------------------------------
-@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4"])
+@pytest.mark.parametrize("cfg", ["C1", "C2", "C3", "C4", "C3b"])
 def test_primary_golden(oracle, golden, cfg):
     g = golden["primary"]
     sc = S.CONFIGS[cfg]()
@@ -143,7 +143,7 @@ def test_primary_survey_vectors(golden):
 
 
 # ---- full renders on the rand() stream ---------------------------------------------------------
-@pytest.mark.parametrize("cfg", ["C1", "C1_noao", "C3", "C2", "C4"])
+@pytest.mark.parametrize("cfg", ["C1", "C1_noao", "C3", "C2", "C4", "C3b"])
 def test_render_libc_golden(oracle, golden, cfg):
     g = golden["render_libc"]
     width, spp, bounces, use_ao = (int(x) for x in g[f"{cfg}_cfg"])

@@ -290,10 +290,23 @@ def tree_mesh(fixture: Optional[str] = None, grid: int = 1) -> Scene:
                  width=1920, spp=500, bounces=6, use_ao=False)
 
 
+def pyramide_eau(fixture: Optional[str] = None) -> Scene:
+    """C3b: the scene main.c ships configured for (main.c:293-322, "refraction stack" renders in results/):
+    model3D/pyramide_eau/scene.obj, 34 triangles, no spheres, materials = ordinals 0 walls, 1 light, 2 floor/ceiling,
+    3 glass, 4 water (the built-in overrides of texture.h:71-87), coordinates up to +-1800; 16:10, 1000 px, vfov 30.2,
+    100 spp, nbRebondMax 20.  Textures: the stripped 1500x1227 PPMs regenerated from the PNGs at 1/4 resolution."""
+    tris, mats, tw, th, nb, quel = mesh_from_fixture(fixture or os.path.join(GOLDEN_DIR, "scene_pyramide_eau.npz"))
+    return Scene(name="pyramide_eau_quarter_res_textures", spheres=np.zeros(0, SPHERE), triangles=tris, mat_list=mats,
+                 tex_w=tw, tex_h=th, nb_materials=nb, quel_mat_pour_tri=quel,
+                 cam_origin=(237.6461, 144.496, -962.8788), cam_target=(-176.9382, 141.5864, 651.8203), vfov=30.2,
+                 ratio=16.0 / 10.0, width=1000, spp=100, bounces=20, use_ao=False)
+
+
 CONFIGS = {
     "C1": cornell_spheres,
     "C2": nature_mesh,
     "C3": nested_dielectrics,
     "C4": tree_mesh,
     "C5": readme_benchmark,
+    "C3b": pyramide_eau,
 }

@@ -91,6 +91,26 @@ def make_scenes(ref: Ref):
         capture_mesh(ref, os.path.join(scratch, "tree_tri.obj"), os.path.join(scratch, "tree_tri.mtl"), "scene_tree.npz")
     finally:
         shutil.rmtree(scratch, ignore_errors=True)
+    # pyramide_eau — the scene main.c itself is configured for (main.c:293-322): 34 triangles whose five materials are
+    # exactly the ordinals texture.h:71-87 overrides (1 light, 3 glass, 4 water); coordinates reach +-1800.
+    # Its five 1500x1227 PPMs are stripped; they are regenerated from the PNGs at 1/4 resolution (nearest) to keep the
+    # fixture small — a REDUCED-TEXTURE variant of the author's scene, labelled as such.
+    scratch = tempfile.mkdtemp(prefix="trt_pyr_")
+    try:
+        src = f"{REFERENCE}/model3D/pyramide_eau"
+        for f in ("scene.obj", "scene.mtl"):
+            shutil.copy(os.path.join(src, f), os.path.join(scratch, f))
+        os.makedirs(os.path.join(scratch, "tex"))
+        for name in ("murs", "lumiere", "plafond_sol", "vitre", "eau"):
+            rgb = Image.open(os.path.join(src, "tex", name + ".png")).convert("RGB")
+            alpha = Image.open(os.path.join(src, "tex", name + "_alpha.png")).convert("L")
+            size = (rgb.size[0] // 4, rgb.size[1] // 4)
+            write_p3(os.path.join(scratch, "tex", name + ".ppm"), np.array(rgb.resize(size, Image.NEAREST)))
+            a = np.array(alpha.resize(size, Image.NEAREST))
+            write_p3(os.path.join(scratch, "tex", name + "_alpha.ppm"), np.repeat(a[..., None], 3, axis=2))
+        capture_mesh(ref, os.path.join(scratch, "scene.obj"), os.path.join(scratch, "scene.mtl"), "scene_pyramide_eau.npz")
+    finally:
+        shutil.rmtree(scratch, ignore_errors=True)
 
 
 # -------------------------------------------------------------------------------------------------
@@ -101,6 +121,7 @@ def golden_primary(ref: Ref):
         "C2": (S.nature_mesh(), 160),
         "C3": (S.nested_dielectrics(), 200),
         "C4": (S.tree_mesh(), 160),
+        "C3b": (S.pyramide_eau(), 160),
     }
     for name, (sc, width) in cases.items():
         rp = S.params_for(sc, width=width, spp=1)
@@ -133,6 +154,7 @@ def golden_renders(ref: Ref):
         "C3": (S.nested_dielectrics(), 80, 6, 19),
         "C2": (S.nature_mesh(), 48, 2, 4),
         "C4": (S.tree_mesh(), 48, 2, 6),
+        "C3b": (S.pyramide_eau(), 64, 4, 20),
     }
     for name, (sc, width, spp, bounces) in cases.items():
         if name.endswith("_noao"):
