@@ -295,9 +295,17 @@ def main():
         fp32_peak = n_sm * 128 * 2 * sm_clock / 1e12                 # TFLOP/s
         achieved = rays_per_launch * f_ray / (kernel_ms * 1e-3) / 1e12
         hbm_alg = 9 * 8 * npix * ((spp + 31) // 32)                 # int64 RED traffic of the flushes, per launch
+        traffic = None
+        try:        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, from the committed ncu capture
+            with open(os.path.join(ROOT, "profiles", "r01_traffic_c2.json")) as f:
+                tj = json.load(f)
+            if args.config == "C2" and spp == sc.spp:
+                traffic = {"bytes_per_launch": tj["traffic_bytes_per_launch"], "source": tj["source"]}
+        except Exception:
+            pass
         roofline = {
             "bound": "fp32", "kernel": "pathtrace_kernel (persistent megakernel, 4-wide BVH)", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-            "frac": achieved / fp32_peak, "traffic": None,
+            "frac": achieved / fp32_peak, "traffic": traffic,
             "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_clock/1e6:.0f} MHz (sm_max_mhz from MEASURED_PEAKS.json, {peak_src})",
             "flops_per_ray": f_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri, "sphere_tests_per_ray": n_sph,
             "rays_per_launch": rays_per_launch, "kernel_ms": kernel_ms,

@@ -173,6 +173,12 @@ TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d
 TRT_API int trt_resolve_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
                                double* d_canva, double* d_albedo, double* d_normal);
 
+/* Un-quantised float3 means (linear radiance before the sqrt tonemap, albedo, normal), W*H*3 floats each, in the
+ * layout OIDN's OIDN_FORMAT_FLOAT3 images use: the hand-off for an external denoiser, instead of the 8-bit round
+ * trip of denoiser.h:43-45. The denoiser itself (denoiser.h:31-91) stays outside this library. */
+TRT_API int trt_resolve_hdr(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                            float* radiance, float* albedo, float* normal);
+
 /* Stream the ctx's first device works on (a cudaStream_t), for callers that interleave their own work. */
 TRT_API void* trt_stream(trt_ctx* ctx);
 TRT_API int   trt_synchronize(trt_ctx* ctx);

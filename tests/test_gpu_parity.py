@@ -218,6 +218,11 @@ def test_bit_identical_across_runs_and_sample_splits(rt):
     c = rt.resolve(S.params_for(sc, width=200, spp=40), total.data_ptr())
     for k in ("canva", "albedo", "normal"):
         assert a[k].tobytes() == c[k].tobytes()
+    # float (HDR) hand-off for a denoiser: sqrt-tonemapping it reproduces canva up to the truncation boundary
+    hdr = rt.resolve_hdr(S.params_for(sc, width=200, spp=40), total.data_ptr())
+    again = np.trunc(256.0 * np.clip(np.sqrt(hdr["radiance"].astype(np.float64)), 0.0, 0.999))
+    assert np.abs(again - a["canva"]).max() <= 1 and (again != a["canva"]).mean() < 0.01
+    assert np.abs(hdr["albedo"] - a["albedo"]).max() < 1e-6 and np.abs(hdr["normal"] - a["normal"]).max() < 1e-6
     # a different seed is a different image
     d = rt.render(S.params_for(sc, width=200, spp=40, seed=7))
     assert d["canva"].tobytes() != a["canva"].tobytes()

@@ -28,7 +28,7 @@ ACCUM_CHANNELS, ACCUM_FRAC_BITS = 9, 28
 # every symbol include/tipe_rt.h declares
 ABI_SYMBOLS = [
     "trt_default_overrides", "trt_init", "trt_destroy", "trt_last_error", "trt_version",
-    "trt_scene_set", "trt_render", "trt_primary", "trt_accumulate", "trt_resolve", "trt_resolve_device",
+    "trt_scene_set", "trt_render", "trt_primary", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr",
     "trt_stream", "trt_synchronize", "trt_bvh_info_get",
     "trt_kat_hit_sphere", "trt_kat_hit_triangle", "trt_kat_refract", "trt_kat_philox", "trt_kat_tonemap",
 ]
@@ -198,6 +198,14 @@ class Renderer:
         p = make_params(rp)
         self._check(self.lib.trt_resolve(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), _ptr(canva), _ptr(albedo), _ptr(normal)), "trt_resolve")
         return dict(canva=canva, albedo=albedo, normal=normal)
+
+    def resolve_hdr(self, rp: RenderParams, d_accum_ptr: int) -> dict:
+        """Un-quantised float32 means for an external denoiser (linear radiance, albedo, normal)."""
+        n = rp.width * rp.height
+        rad, alb, nrm = (np.empty((n, 3), np.float32) for _ in range(3))
+        p = make_params(rp)
+        self._check(self.lib.trt_resolve_hdr(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), _ptr(rad), _ptr(alb), _ptr(nrm)), "trt_resolve_hdr")
+        return dict(radiance=rad, albedo=alb, normal=nrm)
 
     def resolve_device(self, rp: RenderParams, d_accum_ptr: int, d_canva: int, d_albedo: int, d_normal: int):
         p = make_params(rp)

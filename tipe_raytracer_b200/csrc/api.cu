@@ -474,6 +474,26 @@ TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d
     return TRT_OK;
 }
 
+TRT_API int trt_resolve_hdr(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                            float* radiance, float* albedo, float* normal)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    if (!d_accum || !radiance || !albedo || !normal) return fail(ctx, TRT_ERR_INVALID, "NULL buffer");
+    DeviceCtx& d = ctx->devs[0];
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    CU(ctx, cudaSetDevice(d.dev));
+    if ((rc = ensure_out(ctx, d, npix)) != TRT_OK) return rc;
+    float* buf = (float*)d.out;                    // 9*npix doubles are room for 9*npix floats
+    const int divisor = params->sample_total > 0 ? params->sample_total : params->nbRayonParPixel;
+    CU(ctx, trt_launch_resolve_hdr((int)npix, divisor, (const long long*)d_accum, buf, buf + 3 * npix, buf + 6 * npix, d.n_sms, d.stream));
+    CU(ctx, cudaMemcpyAsync(radiance, buf, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaMemcpyAsync(albedo, buf + 3 * npix, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaMemcpyAsync(normal, buf + 6 * npix, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
 TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
                        trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
 {

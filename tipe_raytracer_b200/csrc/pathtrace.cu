@@ -235,6 +235,30 @@ resolve_kernel(ResolveArgs R)
     }
 }
 
+// Un-quantised float3 means (linear radiance, albedo, normal) in OIDN_FORMAT_FLOAT3 layout: what a denoiser wants
+// instead of the 8-bit round trip of denoiser.h:43-45.  The denoiser itself stays external.
+__global__ void __launch_bounds__(256)
+resolve_hdr_kernel(int npix, int divisor, const long long* __restrict__ acc, float* radiance, float* albedo, float* normal)
+{
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < (size_t)npix; p += (size_t)gridDim.x * blockDim.x) {
+        const double k = TRT_ACCUM_INV_SCALE / (double)divisor;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            radiance[3 * p + c] = (float)((double)acc[(size_t)c * npix + p] * k);
+            albedo[3 * p + c] = (float)((double)acc[(size_t)(3 + c) * npix + p] * k);
+            normal[3 * p + c] = (float)((double)acc[(size_t)(6 + c) * npix + p] * k);
+        }
+    }
+}
+
+cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, float* radiance, float* albedo, float* normal, int n_sms, cudaStream_t stream)
+{
+    int grid = (npix + 255) / 256;
+    if (grid > n_sms * 8) grid = n_sms * 8;
+    resolve_hdr_kernel<<<grid, 256, 0, stream>>>(npix, divisor, acc, radiance, albedo, normal);
+    return cudaGetLastError();
+}
+
 // ---- launchers -------------------------------------------------------------------------------------
 template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE = 0>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)

@@ -62,6 +62,7 @@ cudaError_t trt_launch_wavefront(const RenderArgs& A, WfState& S, int n_sms, int
 
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream);
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
+cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, float* radiance, float* albedo, float* normal, int n_sms, cudaStream_t stream);
 
 // K1: FP64 primary visibility, linear scan in the caller's order.
 struct PrimaryArgs {
