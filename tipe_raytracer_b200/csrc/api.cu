@@ -151,6 +151,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 16);
     A.vote = knob("TRT_TUNE_VOTE", 0);
     A.max_hk = knob("TRT_TUNE_MAX_HK", 1);
+    A.item_order = knob("TRT_TUNE_ORDER", 0);
     A.count_tests = count_tests ? 1 : 0;
     A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
     A.wf_check = knob("TRT_TUNE_WF_CHECK", 8);

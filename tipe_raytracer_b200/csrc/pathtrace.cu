@@ -56,7 +56,8 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     int pixel = -1, px = 0, py = 0, s_cur = 0, s_end = 0;
     PathState P;
     P.o = P.d = P.d_ao = P.T = P.L = P.aov_albedo = P.aov_normal = f3(0, 0, 0);
-    P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.src_prim = TRT_NO_PRIM; P.src_twin = -1; P.is_alpha = false;
+    P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.src_prim = TRT_NO_PRIM; P.src_twin = -1; P.is_alpha = false; P.ao_pending = false;
+    const bool fuse_ao = !HAS_TRIS && A.use_ao;      // sphere-only scenes: AO ray + next bounce ray in one scan
     Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
     int stack[TRT_STACK_DEPTH];
     int pend = 0;                           // parked leaf (0 = none), see bvh_trip
@@ -75,7 +76,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
         if (tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)) {
             PathResult res;
-            if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res)) {
+            if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res, fuse_ao)) {
                 my_acc[0 * PT_THREADS] += to_fixed(res.L.x);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z);
                 my_acc[3 * PT_THREADS] += to_fixed(res.albedo.x); my_acc[4 * PT_THREADS] += to_fixed(res.albedo.y); my_acc[5 * PT_THREADS] += to_fixed(res.albedo.z);
                 my_acc[6 * PT_THREADS] += to_fixed(res.normal.x); my_acc[7 * PT_THREADS] += to_fixed(res.normal.y); my_acc[8 * PT_THREADS] += to_fixed(res.normal.z);
@@ -123,10 +124,8 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 if (need) {
                     if (item >= 0 && item < A.n_items) {
                         // item -> (tile, chunk, pixel in tile)
-                        const int p = (int)(item & 31);
-                        const long long tc = item >> 5;
-                        const int chunk = (int)(tc % A.n_chunks);
-                        const int tile = (int)(tc / A.n_chunks);
+                        int p, chunk, tile;
+                        decode_item(A, item, p, chunk, tile);
                         const int tx = tile % A.tiles_x, ty = tile / A.tiles_x;
                         px = tx * 8 + (p & 7); py = ty * 4 + (p >> 3);
                         if (px < W && py < H) {
@@ -155,8 +154,17 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         // ---- A4. new rays: sphere scan, scene-box cull, traversal set-up ---------------------------
         if (new_ray) {
             const bool ao_ray = (phase == PH_AO);
-            ray_begin<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, ao_ray ? P.d_ao : P.d, P.src_prim, P.src_twin, ao_ray, tr, stack, cnt);
-            ray_count++;
+            if (!HAS_TRIS && fuse_ao) {
+                const bool do_bounce = !ao_ray, do_ao = ao_ray || P.ao_pending;
+                bool occluded;
+                spheres_pair<COUNT>(sc, s_sph, P.o, P.d, P.d_ao, do_bounce, do_ao, P.src_prim, tr, occluded, cnt);
+                ray_count += (do_bounce ? 1u : 0u) + (do_ao ? 1u : 0u);
+                if (ao_ray) tr.prim = occluded ? 0 : TRT_NO_PRIM;                              // consumed by consume_hit's AO branch
+                else if (do_ao) { P.T = P.T * (occluded ? A.inv_ao : 0.0f); P.ao_pending = false; }   // main.c:220-221, before the next shading
+            } else {
+                ray_begin<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, P.o, ao_ray ? P.d_ao : P.d, P.src_prim, P.src_twin, ao_ray, tr, stack, cnt);
+                ray_count++;
+            }
         }
         if (!HAS_TRIS || BRUTE || hk + 1 >= A.max_hk) break;
         const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE || pend != 0));

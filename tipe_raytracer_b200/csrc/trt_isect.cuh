@@ -138,6 +138,51 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
     tr.node = sc.root;
 }
 
+// Sphere-only scenes with ambient occlusion: the AO ray of bounce i and the bounce ray of bounce i+1 leave the same
+// point (main.c:162 / main.c:102), so both are resolved in ONE scan that shares oc and c = |oc|^2 - r^2 per sphere.
+// The AO query only needs "any hit" (main.c:106): with t2 = (-hb + sqrt(qd))/a the larger root,
+//   qd > 0 and (t1 >= 1e-4 or t2 >= 1e-4)  <=>  qd > 0 and sqrt(qd) >= 1e-4*a + hb,   no square root needed.
+template <bool COUNT>
+__device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* __restrict__ s_sph, float3 o, float3 d, float3 d_ao,
+                                             bool do_bounce, bool do_ao, int src_prim, Trav& tr, bool& occluded, TraceCounters& cnt)
+{
+    tr.t = __int_as_float(0x7f800000);
+    tr.prim = TRT_NO_PRIM;
+    tr.u = tr.v = 0.0f;
+    tr.node = TRT_TRAV_DONE;
+    tr.sp = 0;
+    occluded = false;
+    const float a = dot3(d, d), inv_a = __frcp_rn(a);
+    const float a2 = dot3(d_ao, d_ao), eps2 = 1e-4f * a2;
+    const int ns = sc.n_spheres;
+    for (int k = 0; k < ns; k++) {
+        const float4 cr = s_sph[k];
+        const float3 oc = f3(o.x - cr.x, o.y - cr.y, o.z - cr.z);
+        float c = fmaf(oc.x, oc.x, fmaf(oc.y, oc.y, fmaf(oc.z, oc.z, -cr.w * cr.w)));
+        if (k == src_prim) c = 0.0f;
+        if (do_bounce) {
+            const float hb = dot3(oc, d);
+            const float qd = fmaf(hb, hb, -a * c);
+            if (qd > 0.0f) {
+                const float sq = qd * rsqrtf(qd);
+                const float q = -(hb + copysignf(sq, hb));
+                const float ra = q * inv_a;
+                const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
+                const float t1 = fminf(ra, rb), t2 = fmaxf(ra, rb);
+                const float t = (t1 >= 1e-4f) ? t1 : ((t2 >= 1e-4f) ? t2 : -1.0f);
+                if (t >= 0.0f && t < tr.t) { tr.t = t; tr.prim = k; }
+            }
+        }
+        if (do_ao) {
+            const float hb = dot3(oc, d_ao);
+            const float qd = fmaf(hb, hb, -a2 * c);
+            const float e = eps2 + hb;
+            occluded = occluded || (qd > 0.0f && (e <= 0.0f || qd >= e * e));
+        }
+    }
+    if (COUNT) cnt.sphere_tests += ns * ((do_bounce ? 1 : 0) + (do_ao ? 1 : 0));
+}
+
 // One visit of a 4-wide node for a lane with tr.node >= 0 (and != TRT_TRAV_DONE): four slab tests,
 // children that are hit are ordered by entry distance (5-comparator network), the nearest is
 // visited next and the others pushed farthest first.

@@ -19,11 +19,25 @@ struct PathState {
     int    alpha_depth;
     int    src_prim, src_twin;
     bool   is_alpha;
+    bool   ao_pending;      // fused mode: the AO ray of the last shaded bounce is traced together with the next bounce ray
 };
 
 struct PathResult {         // what one finished path adds to its pixel (col_alb_norm, denoiser.h:11-13)
     float3 L, albedo, normal;
 };
+
+// item index -> (pixel slot p of an 8x4 tile, sample chunk, tile).  An item is (pixel, chunk of samples); 32*n_chunks
+// consecutive items cover one tile.  order 0: pixel fastest (32 consecutive items = the 32 pixels of the tile, one
+// chunk); order 1: chunk fastest (32 consecutive items = all chunks of 2-3 neighbouring pixels, so the lanes of a warp
+// start on nearly identical primary rays: coherent traversal, node fetches that coalesce).
+__device__ __forceinline__ void decode_item(const RenderArgs& A, long long item, int& p, int& chunk, int& tile)
+{
+    const int per_tile = 32 * A.n_chunks;
+    tile = (int)(item / per_tile);
+    const int local = (int)(item - (long long)tile * per_tile);
+    if (A.item_order == 0) { p = local & 31; chunk = local >> 5; }
+    else { chunk = local % A.n_chunks; p = local / A.n_chunks; }
+}
 
 // fill_canva's per-sample set-up (main.c:265-271) + get_ray (camera.h:42-54).
 // A.cam_corner = coin_bas_gauche - origin, formed in FP64 on the host.
@@ -42,6 +56,7 @@ __device__ __forceinline__ void start_path(const RenderArgs& A, int pixel, int p
     P.aov_albedo = P.aov_normal = f3(0, 0, 0);
     P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.is_alpha = false;
     P.src_prim = TRT_NO_PRIM; P.src_twin = -1;
+    P.ao_pending = false;
 }
 
 // One completed closest_hit query -> one trip of the bounce loop (main.c:132-239) or the end of an
@@ -51,7 +66,7 @@ __device__ __forceinline__ void start_path(const RenderArgs& A, int pixel, int p
 // sph / sph_mat may point to shared or global memory.
 __device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* __restrict__ sph, const float4* __restrict__ sph_mat,
                                             int pixel, int sample, float hit_t, int hit_prim, float hit_u, float hit_v,
-                                            PathState& P, int& phase, PathResult& res)
+                                            PathState& P, int& phase, PathResult& res, bool fuse_ao = false)
 {
     const DevScene& sc = A.scene;
     const bool did_hit = hit_prim != TRT_NO_PRIM;
@@ -133,7 +148,8 @@ __device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* _
         P.T = m.diffuse * P.T;
         if (A.use_ao) {
             P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                             // main.c:100-102
-            phase = PH_AO;
+            if (fuse_ao) { P.ao_pending = true; if (P.bounce >= A.bounces) phase = PH_AO; }       // AO ray rides with the next bounce ray
+            else phase = PH_AO;
         }
     }
     res.L = P.L;
