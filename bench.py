@@ -53,38 +53,61 @@ def workload(name: str):
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons WHILE the timed region runs (B200_PROFILING.md recipe).  NVML is polled in-process
+    every 5 ms (a timed step is ~40 ms; forking nvidia-smi takes longer than that); nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], threading.Event()
+        self.gpu, self.stop_flag = gpu_index, threading.Event()
+        self.sm, self.sm_max, self.reasons, self.source = [], [], set(), "nvml"
+        self.h = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def _poll_nvml(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        self.sm_max.append(float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for bit, nm in ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap")):
+            if r & bit:
+                self.reasons.add(nm)
+
+    def _poll_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout.strip()
+        r = [c.strip() for c in out.split(",")]
+        if len(r) > 8:
+            self.sm.append(float(r[1])); self.sm_max.append(float(r[2]))
+            for k, nm in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+                if r[5 + k].lower().startswith("active"):
+                    self.reasons.add(nm)
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
+                if self.h is not None:
+                    self._poll_nvml()
+                else:
+                    self._poll_smi()
             except Exception:
-                pass
-            self.stop_flag.wait(0.2)
+                if self.h is not None:
+                    self.h, self.source = None, "nvidia-smi"
+            self.stop_flag.wait(0.005 if self.h is not None else 0.2)
 
     def summary(self):
         self.stop_flag.set()
         self.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            for k, nm in enumerate(names):
-                if len(r) > 5 + k and r[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.sm_max) if self.sm_max else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def measured_peaks():

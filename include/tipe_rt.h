@@ -186,6 +186,9 @@ TRT_API int   trt_synchronize(trt_ctx* ctx);
 /* BVH facts of the current scene: nodes, leaves, max depth, root surface-area cost. */
 typedef struct trt_bvh_info { int n_nodes, n_leaves, max_depth, n_twins; double sah_cost; double ms_build; } trt_bvh_info;
 TRT_API int trt_bvh_info_get(trt_ctx* ctx, trt_bvh_info* out);
+/* Scheduling counters of the last TRT_FLAG_COUNT_TESTS launch (tools/): BVH-loop trips per warp, lanes inside / at a node /
+   at a leaf summed over trips, loop sessions, housekeeping passes, lanes consuming a hit summed over passes. */
+TRT_API int trt_debug_schedule(trt_ctx* ctx, uint64_t* out7);
 
 /* ---- device known-answer entry points (FP32 leaf functions of the path-tracing kernel,
  *      run on the GPU over n independent inputs; outputs are float) -------------------------- */

@@ -29,7 +29,7 @@ ACCUM_CHANNELS, ACCUM_FRAC_BITS = 9, 28
 ABI_SYMBOLS = [
     "trt_default_overrides", "trt_init", "trt_destroy", "trt_last_error", "trt_version",
     "trt_scene_set", "trt_render", "trt_primary", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr",
-    "trt_stream", "trt_synchronize", "trt_bvh_info_get",
+    "trt_stream", "trt_synchronize", "trt_bvh_info_get", "trt_debug_schedule",
     "trt_kat_hit_sphere", "trt_kat_hit_triangle", "trt_kat_refract", "trt_kat_philox", "trt_kat_tonemap",
 ]
 
@@ -211,6 +211,11 @@ class Renderer:
         p = make_params(rp)
         self._check(self.lib.trt_resolve_device(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(d_canva),
                                                 C.c_void_p(d_albedo), C.c_void_p(d_normal)), "trt_resolve_device")
+
+    def debug_schedule(self) -> dict:
+        out = (C.c_uint64 * 7)()
+        self._check(self.lib.trt_debug_schedule(self.ctx, out), "trt_debug_schedule")
+        return dict(zip(("trips", "inside", "node", "leaf", "sessions", "hk", "consume"), [int(x) for x in out]))
 
     def stream_ptr(self) -> int:
         return int(self.lib.trt_stream(self.ctx) or 0)

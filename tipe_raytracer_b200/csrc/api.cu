@@ -151,11 +151,11 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 16);
     A.vote = knob("TRT_TUNE_VOTE", 0);
     A.max_hk = knob("TRT_TUNE_MAX_HK", 1);
-    A.item_order = knob("TRT_TUNE_ORDER", 0);
+    A.item_order = knob("TRT_TUNE_ORDER", d.scene.n_tris > 0 ? 1 : 0);   // meshes: a warp starts on the samples of 2-3 neighbouring pixels (coherent primary rays, +2-3 %); spheres: one tile (+5 %)
     A.count_tests = count_tests ? 1 : 0;
     A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
     A.wf_check = knob("TRT_TUNE_WF_CHECK", 8);
-    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (3 CTAs of 256 threads per SM, 80 registers)
+    const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (4 CTAs of 256 threads per SM, 64 registers)
     A.chunk = spp < chunk_max ? spp : chunk_max;
     A.n_chunks = (spp + A.chunk - 1) / A.chunk;
     A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;
@@ -163,7 +163,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.item_counter = d.ctrs;
     A.counters = d.ctrs + 1;
     A.accum = accum;
-    CU(ctx, cudaMemsetAsync(d.ctrs, 0, sizeof(unsigned long long) * 8, d.stream));
+    CU(ctx, cudaMemsetAsync(d.ctrs, 0, sizeof(unsigned long long) * 16, d.stream));
     if (engine == 2) {
         const long long real_items = (long long)A.W * A.H * A.n_chunks;
         long long want = knob("TRT_TUNE_SLOTS", 1 << 20);
@@ -179,7 +179,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
         WfState S{};
         trt_wavefront_carve(d.wf_buf, n_slots, S);
         CU(ctx, cudaEventRecord(d.ev_a, d.stream));
-        CU(ctx, trt_launch_wavefront(A, S, d.n_sms, (int*)&d.h_ctrs[7], &d.last_launches, d.stream));
+        CU(ctx, trt_launch_wavefront(A, S, d.n_sms, (int*)&d.h_ctrs[15], &d.last_launches, d.stream));
         CU(ctx, cudaEventRecord(d.ev_b, d.stream));
     } else {
         CU(ctx, cudaEventRecord(d.ev_a, d.stream));
@@ -187,7 +187,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
         CU(ctx, cudaEventRecord(d.ev_b, d.stream));
         d.last_launches = 1;
     }
-    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 7, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 12, cudaMemcpyDeviceToHost, d.stream));
     return TRT_OK;
 }
 
@@ -259,8 +259,8 @@ TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
             (e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev_a)) != cudaSuccess || (e = cudaEventCreate(&d.ev_b)) != cudaSuccess ||
             (e = cudaEventCreate(&d.ev_c)) != cudaSuccess || (e = cudaEventCreate(&d.ev_d)) != cudaSuccess ||
-            (e = cudaMalloc(&d.ctrs, sizeof(unsigned long long) * 8)) != cudaSuccess ||
-            (e = cudaMallocHost(&d.h_ctrs, sizeof(unsigned long long) * 8)) != cudaSuccess) {
+            (e = cudaMalloc(&d.ctrs, sizeof(unsigned long long) * 16)) != cudaSuccess ||
+            (e = cudaMallocHost(&d.h_ctrs, sizeof(unsigned long long) * 16)) != cudaSuccess) {
             fail(nullptr, TRT_ERR_CUDA, "device %d set-up failed: %s", d.dev, cudaGetErrorString(e));
             trt_destroy(ctx);
             return TRT_ERR_CUDA;
@@ -271,7 +271,7 @@ TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
             return TRT_ERR_NO_DEVICE;
         }
         d.n_sms = prop.multiProcessorCount;
-        memset(d.h_ctrs, 0, sizeof(unsigned long long) * 8);
+        memset(d.h_ctrs, 0, sizeof(unsigned long long) * 16);
     }
     // peer access root <- others, for the fused reduce+resolve
     for (size_t k = 1; k < ctx->devs.size(); k++) {
@@ -406,6 +406,16 @@ TRT_API int trt_bvh_info_get(trt_ctx* ctx, trt_bvh_info* out)
     return TRT_OK;
 }
 
+// Schedule counters of the last TRT_FLAG_COUNT_TESTS launch on device 0 (tools/ only; see pathtrace.cu):
+// [0] BVH-loop trips (per warp) [1] lanes inside, summed over trips [2] lanes at a node [3] lanes at a leaf
+// [4] loop sessions [5] housekeeping passes [6] lanes consuming a hit, summed over passes
+TRT_API int trt_debug_schedule(trt_ctx* ctx, uint64_t* out7)
+{
+    if (!ctx || !out7) return TRT_ERR_INVALID;
+    for (int k = 0; k < 7; k++) out7[k] = ctx->devs[0].h_ctrs[5 + k];
+    return TRT_OK;
+}
+
 TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_accum, trt_stats* stats)
 {
     int rc = check_params(ctx, params);
@@ -520,7 +530,7 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
         } else {
             CU(ctx, cudaEventRecord(d.ev_a, d.stream));
             CU(ctx, cudaEventRecord(d.ev_b, d.stream));
-            memset(d.h_ctrs, 0, sizeof(unsigned long long) * 8);
+            memset(d.h_ctrs, 0, sizeof(unsigned long long) * 16);
         }
         CU(ctx, cudaEventRecord(d.ev_c, d.stream));
         srcs.push_back(d.accum);

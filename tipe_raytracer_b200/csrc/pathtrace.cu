@@ -20,7 +20,7 @@
 
 #define PT_THREADS 256
 #ifndef PT_MIN_BLOCKS
-#define PT_MIN_BLOCKS 3
+#define PT_MIN_BLOCKS 4           // 64 registers, 32 warps/SM: measured 1-6 % faster than 3 CTAs at 80 registers on C1/C2/C4 (154 B of spills)
 #endif
 #define PT_POOL 32
 // Traversal-loop exit policy (RenderArgs.min_steps / exit_num): a warp always takes min_steps BVH steps,
@@ -60,10 +60,14 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     const bool fuse_ao = !HAS_TRIS && A.use_ao;      // sphere-only scenes: AO ray + next bounce ray in one scan
     Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
     int stack[TRT_STACK_DEPTH];
-    int pend = 0;                           // parked leaf (0 = none), see bvh_trip
+    float stack_t[MODE == 3 ? TRT_STACK_DEPTH : 1];   // entry distances of the stacked children (MODE 3: culled at pop time)
+    int pend = 0;                           // parked leaf (0 = none), see bvh_trip / bvh_step_dual
 
     unsigned ray_count = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
+    // schedule counters (COUNT builds only, warp-uniform): BVH-loop trips, lanes inside / at a node / at a leaf per trip,
+    // loop sessions, housekeeping passes, lanes consuming a hit per pass
+    unsigned long long sc_trips = 0, sc_inside = 0, sc_node = 0, sc_leaf = 0, sc_sessions = 0, sc_hk = 0, sc_consume = 0;
 
     for (;;) {
       // ---- A. housekeeping, repeated (up to max_hk passes) while too few lanes have BVH work: lanes whose
@@ -72,6 +76,10 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
       unsigned live_mask = 0;
       for (int hk = 0;; hk++) {
         bool new_ray = false;
+        if (COUNT) {
+            sc_hk++;
+            sc_consume += __popc(__ballot_sync(0xffffffffu, tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)));
+        }
 
         // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
         if (tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)) {
@@ -186,8 +194,17 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
                 if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
+                if (COUNT) {
+                    if (step == 0) sc_sessions++;
+                    sc_trips++; sc_inside += __popc(in_mask);
+                    sc_node += __popc(__ballot_sync(0xffffffffu, tr.node >= 0 && tr.node != TRT_TRAV_DONE));
+                    sc_leaf += __popc(__ballot_sync(0xffffffffu, MODE >= 1 ? pend != 0 : tr.node < 0));
+                }
                 if (MODE == 1) {
                     bvh_trip<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, inside, tr, pend, stack, cnt);
+                } else if (MODE >= 2) {
+                    // node visit + parked leaf test in the same trip
+                    if (inside) bvh_step_dual<COUNT, MODE == 3>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, pend, stack, stack_t, cnt);
                 } else {
                     // if-if: every trip, each lane does whatever it is at (measured faster than deferral on B200)
                     if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
@@ -209,7 +226,12 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             t += __shfl_xor_sync(0xffffffffu, t, off);
             s += __shfl_xor_sync(0xffffffffu, s, off);
         }
-        if (lane == 0) { atomicAdd(A.counters + 1, b); atomicAdd(A.counters + 2, t); atomicAdd(A.counters + 3, s); }
+        if (lane == 0) {
+            atomicAdd(A.counters + 1, b); atomicAdd(A.counters + 2, t); atomicAdd(A.counters + 3, s);
+            atomicAdd(A.counters + 4, sc_trips); atomicAdd(A.counters + 5, sc_inside); atomicAdd(A.counters + 6, sc_node);
+            atomicAdd(A.counters + 7, sc_leaf); atomicAdd(A.counters + 8, sc_sessions); atomicAdd(A.counters + 9, sc_hk);
+            atomicAdd(A.counters + 10, sc_consume);
+        }
     }
 }
 
@@ -284,9 +306,19 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
-    if (count_tests) return launch_variant<true, false, true>(A, grid, smem, stream);
-    return A.vote ? launch_variant<true, false, false, 1>(A, grid, smem, stream)
-                  : launch_variant<true, false, false, 0>(A, grid, smem, stream);
+    if (count_tests) {
+        switch (A.vote) {
+            case 2: return launch_variant<true, false, true, 2>(A, grid, smem, stream);
+            case 3: return launch_variant<true, false, true, 3>(A, grid, smem, stream);
+            default: return launch_variant<true, false, true, 0>(A, grid, smem, stream);
+        }
+    }
+    switch (A.vote) {
+        case 1: return launch_variant<true, false, false, 1>(A, grid, smem, stream);
+        case 2: return launch_variant<true, false, false, 2>(A, grid, smem, stream);
+        case 3: return launch_variant<true, false, false, 3>(A, grid, smem, stream);
+        default: return launch_variant<true, false, false, 0>(A, grid, smem, stream);
+    }
 }
 
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream)

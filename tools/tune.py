@@ -32,4 +32,4 @@ for combo in itertools.product(*[grid[k] for k in keys]):
         st = r.accumulate(rp, acc.data_ptr())
         best = min(best, st["ms_trace"])
     tag = " ".join(f"{k.replace('TRT_TUNE_', '').replace('TRT_', '')}={v}" for k, v in zip(keys, combo))
-    print(f"{cfg} {tag} ms={best:.2f} Mrays/s={st['rays']/best/1e3:.0f} rays/path={st['rays']/st['paths']:.3f} launches={st['kernel_launches']}", flush=True)
+    print(f"{cfg} {tag} ms={best:.2f} Mrays/s={st['rays']/best/1e3:.0f} rays/path={st['rays']/st['paths']:.3f} launches={st['kernel_launches']} checksum={int(acc.sum().item())}", flush=True)
