@@ -8,6 +8,7 @@
  *   main_b200 [--scene readme|sky|none] [--obj F --mtl F] [--width W] [--ratio R] [--spp N] [--bounces N]
  *             [--ao 0|1] [--ao-intensity X] [--vfov D] [--origin x,y,z] [--target x,y,z] [--focus F]
  *             [--aperture ax,ay] [--seed S] [--gpus N] [--no-main-c-truncation] [--out file.ppm]
+ *             [--sky-image F.ppm]   lat-long sky on the LAST sphere (the lookup main.c:64-71 keeps commented out; sky_file, main.c:322)
  *
  * Build: gcc -O2 apps/main_b200.c -o apps/main_b200 -Ltipe_raytracer_b200 -ltipe_rt -lm -Wl,-rpath,'$ORIGIN/../tipe_raytracer_b200'
  */
@@ -38,7 +39,7 @@ int main(int argc, char** argv)
     double focus_distance = 3, ouverture[2] = {0.0, 0.0};
     int nbRayonParPixel = 100, nbRebondMax = 5;
     int useAO = 1; double AO_intensity = 2.5;
-    const char *obj_file = NULL, *mtl_file = NULL, *scene = "readme", *out_file = "out_b200.ppm";
+    const char *obj_file = NULL, *mtl_file = NULL, *scene = "readme", *out_file = "out_b200.ppm", *sky_file = NULL;
     unsigned long long seed = 1010; int n_gpus = 1, truncate_like_main_c = 1;
 
     for (int k = 1; k < argc; k++) {
@@ -52,6 +53,7 @@ int main(int argc, char** argv)
         else if (OPT("--origin")) { if (parse3(v, origin, 3)) goto usage; } else if (OPT("--target")) { if (parse3(v, target, 3)) goto usage; }
         else if (OPT("--aperture")) { if (parse3(v, ouverture, 2)) goto usage; }
         else if (OPT("--seed")) seed = strtoull(v, NULL, 10); else if (OPT("--gpus")) n_gpus = atoi(v); else if (OPT("--out")) out_file = v;
+        else if (OPT("--sky-image")) sky_file = v;
         else if (strcmp(a, "--no-main-c-truncation") == 0) truncate_like_main_c = 0;
         else { usage: fprintf(stderr, "usage: see the header of apps/main_b200.c (bad option `%s`)\n", a); return 2; }
     }
@@ -105,6 +107,12 @@ int main(int argc, char** argv)
                       mesh.nbMaterials, mesh.quelMatPourTri, NULL, -1) != TRT_OK) {
         fprintf(stderr, "trt_scene_set: %s\n", trt_last_error(ctx)); return 1;
     }
+    trt_material* sky_mat_list = NULL; int sky_width = 0, sky_height = 0;
+    if (sky_file) {                                            /* create_mat_list(sky_file, ...), main.c:373-374 */
+        sky_mat_list = trt_load_sky(sky_file, &sky_width, &sky_height, err);
+        if (!sky_mat_list) { fprintf(stderr, "%s\n", err); return 1; }
+        if (trt_sky_set(ctx, sky_mat_list, sky_width, sky_height) != TRT_OK) { fprintf(stderr, "trt_sky_set: %s\n", trt_last_error(ctx)); return 1; }
+    }
     trt_params p; memset(&p, 0, sizeof p);
     p.largeur_image = largeur_image; p.hauteur_image = hauteur_image;
     p.nbRayonParPixel = nbRayonParPixel; p.nbRebondMax = nbRebondMax;
@@ -129,7 +137,7 @@ int main(int argc, char** argv)
            (double)st.rays / t_render / 1e6, now_s() - t_start, out_file);
 
     trt_destroy(ctx);
-    free(canva); free(albedo_tab); free(normal_tab); free(mat_list);
+    free(canva); free(albedo_tab); free(normal_tab); free(mat_list); free(sky_mat_list);
     trt_free_mesh(&mesh);
     return 0;
 }

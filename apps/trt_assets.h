@@ -257,6 +257,28 @@ static trt_material* trt_load_textures(char** texture_paths, int nbMaterials, in
     return out;
 }
 
+/* Sky image, like create_mat_list (texture.h:145-173): sky_w*sky_h materials whose diffuseColor is the P3 texel / maxVal,
+ * file row 0 (top) stored last, every other field 0.  For trt_sky_set. */
+static trt_material* trt_load_sky(const char* path, int* sky_w, int* sky_h, char* err)
+{
+    int w = 0, h = 0, mx = 0;
+    int* c = trt__read_p3(path, &w, &h, &mx, err);
+    if (!c) return NULL;
+    trt_material* out = (trt_material*)calloc((size_t)w * h, sizeof(trt_material));
+    if (!out) { snprintf(err, 256, "out of memory for a %dx%d sky", w, h); free(c); return NULL; }
+    for (int row = 0; row < h; row++) {
+        const int i = h - 1 - row;
+        for (int j = 0; j < w; j++) {
+            const int* px = c + ((size_t)row * w + j) * 3;
+            trt_material* m = &out[(size_t)i * w + j];
+            m->diffuseColor.e[0] = (double)px[0] / mx; m->diffuseColor.e[1] = (double)px[1] / mx; m->diffuseColor.e[2] = (double)px[2] / mx;
+        }
+    }
+    free(c);
+    *sky_w = w; *sky_h = h;
+    return out;
+}
+
 /* init_camera (camera.h:17-40), same operation order. */
 static trt_camera trt_init_camera(const double origin[3], const double target[3], const double up[3], double vfov, double ratio)
 {

@@ -148,6 +148,13 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
                           const int* quelMatPourTri,
                           const trt_mat_override* overrides, int n_overrides);
 
+/* Sky environment: enables the lat-long lookup the reference keeps commented out at main.c:64-71 (sphere_uvmapping,
+ * texture.h:92-112; sky_mat_list as loaded by create_mat_list, texture.h:145-173: sky_w*sky_h materials whose
+ * diffuseColor is the texel, index y*sky_w + x with row 0 = bottom PPM row).  The LAST sphere of the scene then emits
+ * the texel under the hit point (emissionColor = texel, alpha = 1), like ThreadData.sky_mat_list (main.c:29,34) would.
+ * NULL switches it off (the default: main.c as shipped).  Independent of trt_scene_set; kept until changed. */
+TRT_API int trt_sky_set(trt_ctx* ctx, const trt_material* sky_mat_list, int sky_width, int sky_height);
+
 /* ---- the drop-in call: replaces main.c:402-453 ------------------------------------------- */
 /* canva / albedo_tab / normal_tab: caller-owned host arrays of W*H colors; stats may be NULL. */
 TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,

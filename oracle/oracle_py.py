@@ -72,6 +72,7 @@ class OracleScene(C.Structure):
         ("mat_list", C.c_void_p), ("tex_w", C.c_int), ("tex_h", C.c_int),
         ("quelMatPourTri", C.c_void_p),
         ("overrides", C.c_void_p), ("n_overrides", C.c_int),
+        ("sky_mat_list", C.c_void_p), ("sky_w", C.c_int), ("sky_h", C.c_int),
     ]
 
 
@@ -113,6 +114,12 @@ class Oracle:
             ov = np.ascontiguousarray(scene.overrides)
             keep = keep + (ov,)
             sc.overrides, sc.n_overrides = _ptr(ov), ov.shape[0]
+        if getattr(scene, "sky_mat_list", None) is not None:
+            sky = np.ascontiguousarray(scene.sky_mat_list)
+            keep = keep + (sky,)
+            sc.sky_mat_list, sc.sky_w, sc.sky_h = _ptr(sky), scene.sky_w, scene.sky_h
+        else:
+            sc.sky_mat_list, sc.sky_w, sc.sky_h = None, 0, 0
         return sc, keep
 
     def render(self, scene, rp, rng=RNG_PHILOX, threads=0, want_sums=False):
@@ -179,6 +186,11 @@ class Oracle:
         self.lib.oracle_tri_uvmapping(C.byref(sc), C.c_int(tri_index), _ptr(point), _ptr(normal), _ptr(out))
         del keep
         return out[0]
+
+    def sphere_uvmapping(self, center, radius, point, sky_w, sky_h) -> int:
+        center, point = (np.asarray(x, np.float64).copy() for x in (center, point))
+        self.lib.oracle_sphere_uvmapping.restype = C.c_int
+        return int(self.lib.oracle_sphere_uvmapping(_ptr(center), C.c_double(radius), _ptr(point), C.c_int(sky_w), C.c_int(sky_h)))
 
     def reflect(self, v, n):
         v, n = (np.asarray(x, np.float64).copy() for x in (v, n)); out = np.zeros(3)
@@ -317,6 +329,15 @@ class Ref:
         self.lib.ref_kat_tri_uvmapping(_ptr(one), _ptr(point), _ptr(normal), _ptr(mats), C.c_int(scene.tex_w),
                                        C.c_int(scene.tex_h), C.c_int(tri_index), _ptr(quel), _ptr(out))
         return out[0]
+
+    def sphere_uvmapping(self, center, radius, point, sky_w, sky_h) -> int:
+        """texel index sphere_uvmapping (texture.h:92-112) reads, recovered through a sky whose texel k has diffuse.r = k."""
+        from tipe_raytracer_b200.scene import MATERIAL, SPHERE
+        s = np.zeros(1, SPHERE); s[0]["center"] = center; s[0]["radius"] = radius
+        sky = np.zeros(sky_w * sky_h, MATERIAL); sky["diffuseColor"][:, 0] = np.arange(sky_w * sky_h)
+        point = np.asarray(point, np.float64).copy(); out = np.zeros(1, MATERIAL)
+        self.lib.ref_kat_sphere_uvmapping(_ptr(s), _ptr(point), _ptr(sky), C.c_int(sky_w), C.c_int(sky_h), _ptr(out))
+        return int(out[0]["diffuseColor"][0])
 
     def reflect(self, v, n):
         v, n = (np.asarray(x, np.float64).copy() for x in (v, n)); out = np.zeros(3)

@@ -186,6 +186,15 @@ REF_API void ref_kat_tri_uvmapping(const triangle* tri, const double* point, con
     *out = tri_uvmapping(*tri, h, (material*)mat_list, tw, th, tri_index, (int*)quelMat);
 }
 
+/* sphere_uvmapping (texture.h:92-112) is compiled into the reference but its call site is commented out (main.c:65-71):
+ * it can be pinned as a function, not through a render. */
+REF_API void ref_kat_sphere_uvmapping(const sphere* s, const double* point, const material* sky_mat_list, int w, int h, material* out)
+{
+    HitInfo hi; memset(&hi, 0, sizeof hi); hi.didHit = true;
+    memcpy(hi.hitPoint.e, point, 24);
+    *out = sphere_uvmapping(*s, hi, (material*)sky_mat_list, w, h);
+}
+
 REF_API void ref_kat_reflect(const double* v, const double* n, double* out)
 {
     vec3 a = {{v[0], v[1], v[2]}}, b = {{n[0], n[1], n[2]}};

@@ -213,6 +213,25 @@ static trt_material texel_material(const oracle_scene* sc, int tri_index, v3 P, 
     return m;
 }
 
+/* sphere_uvmapping (texture.h:92-112): lat-long texel of the sky image under a hit point on sphere (c, r).
+ * The reference indexes mat_list unchecked; theta = pi (straight down) or phi = 2*pi would read one row / one texel
+ * past the intended one, so the index is clamped to the last texel here and on the GPU. */
+static int sky_texel_index(v3 center, double radius, v3 P, int sky_w, int sky_h)
+{
+    const double PI_ = 3.1415926535897932385;              /* rtutility.h:12 */
+    v3 d = vdiv(vsub(P, center), radius);
+    double theta = acos(-d.x[1]);
+    double phi = atan2(-d.x[2], d.x[0]) + PI_;
+    double u = phi / (2 * PI_);
+    double v = theta / PI_;
+    int x = (int)(u * (double)sky_w);
+    int y = (int)(v * (double)sky_h);
+    long index = (long)y * sky_w + x;
+    if (index < 0) index = 0;
+    if (index > (long)sky_w * sky_h - 1) index = (long)sky_w * sky_h - 1;
+    return (int)index;
+}
+
 typedef struct { uint64_t rays, sphere_tests, tri_tests; } counters_t;
 
 /* main.c:52-92 — spheres first, then triangles, strict '<' so the first primitive wins ties.
@@ -226,7 +245,14 @@ static hit_t nearest_hit(const oracle_scene* sc, v3 o, v3 d, counters_t* cnt, in
     if (cnt) { cnt->rays++; cnt->sphere_tests += (uint64_t)sc->nbSpheres; cnt->tri_tests += (uint64_t)sc->nbTriangles; }
     for (int k = 0; k < sc->nbSpheres; k++) {
         hit_t h = sphere_hit(from_trt(&sc->spheres[k].center), sc->spheres[k].radius, o, d);
-        if (h.hit && h.dst < best.dst) { best = h; best.mat = sc->spheres[k].mat; id = k; }
+        if (h.hit && h.dst < best.dst) {
+            best = h; best.mat = sc->spheres[k].mat; id = k;
+            if (sc->sky_mat_list && k == sc->nbSpheres - 1) {          /* "cas du ciel", main.c:64-71 (commented out upstream) */
+                int index = sky_texel_index(from_trt(&sc->spheres[k].center), sc->spheres[k].radius, h.point, sc->sky_w, sc->sky_h);
+                best.mat.emissionColor = sc->sky_mat_list[index].diffuseColor;
+                best.mat.alpha = 1.0;
+            }
+        }
     }
     for (int k = 0; k < sc->nbTriangles; k++) {
         hit_t h = triangle_hit(&sc->tris[k], o, d);
@@ -578,6 +604,9 @@ API int oracle_hit_triangle(const trt_triangle* tri, const double* o, const doub
 API void oracle_tri_uvmapping(const oracle_scene* sc, int tri_index, const double* point, const double* normal,
                               trt_material* out)
 { *out = texel_material(sc, tri_index, from_ptr(point), from_ptr(normal)); }
+
+API int oracle_sphere_uvmapping(const double* center, double radius, const double* point, int sky_w, int sky_h)
+{ return sky_texel_index(from_ptr(center), radius, from_ptr(point), sky_w, sky_h); }
 
 API void oracle_reflect(const double* v, const double* n, double* out)
 { to_ptr(reflect_dir(from_ptr(v), from_ptr(n)), out); }

@@ -30,6 +30,9 @@ typedef struct oracle_scene {
     const trt_material* mat_list;  int tex_w, tex_h;
     const int*          quelMatPourTri;
     const trt_mat_override* overrides; int n_overrides;   /* NULL / <0 => reference built-ins */
+    /* Sky environment: the lat-long lookup the reference keeps commented out at main.c:65-71.
+     * NULL => exactly main.c as shipped.  Non-NULL => the LAST sphere takes emissionColor from the sky texel, alpha = 1. */
+    const trt_material* sky_mat_list; int sky_w, sky_h;
 } oracle_scene;
 
 typedef struct oracle_stats {
@@ -58,6 +61,7 @@ int  oracle_hit_triangle(const trt_triangle* tri, const double* o, const double*
                          double* dst, double* point, double* normal);                /* mesh.h:70-94 */
 void oracle_tri_uvmapping(const oracle_scene* sc, int tri_index, const double* point, const double* normal,
                           trt_material* out);                                        /* texture.h:44-90 */
+int  oracle_sphere_uvmapping(const double* center, double radius, const double* point, int sky_w, int sky_h); /* texture.h:92-112, texel index */
 void oracle_reflect(const double* v, const double* n, double* out);                  /* rtutility.h:205-208 */
 void oracle_refract(const double* v, const double* n, double n1, double n2, double* out); /* rtutility.h:210-227 */
 void oracle_tonemap(const double* sum, int spp, double* out);                        /* rtutility.h:56-71 */

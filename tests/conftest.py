@@ -34,7 +34,7 @@ def ref():
 
 @pytest.fixture(scope="session")
 def golden():
-    return {name: np.load(os.path.join(GOLDEN, f"golden_{name}.npz")) for name in ("leaves", "primary", "render_libc")}
+    return {name: np.load(os.path.join(GOLDEN, f"golden_{name}.npz")) for name in ("leaves", "primary", "render_libc", "sky")}
 
 
 @pytest.fixture(scope="session")

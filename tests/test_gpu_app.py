@@ -66,6 +66,20 @@ def test_c_host_program_renders_the_same_image(rt, tmp_path):
     img, w, h = read_ppm(out)
     rt.scene_set(sc)
     assert np.array_equal(img, rt.render(S.params_for(sc))["canva"])
+    # sky image through the C loader (create_mat_list's layout) and trt_sky_set
+    sky_sc = mini_scene()
+    sky_sc.sky_w, sky_sc.sky_h = 64, 32
+    sky_sc.sky_mat_list = S.procedural_sky(64, 32)
+    rows = (sky_sc.sky_mat_list["diffuseColor"].reshape(32, 64, 3) * 255.0 + 0.5).astype(int)[::-1]      # file row 0 = top
+    sky_ppm = tmp_path / "sky.ppm"
+    sky_ppm.write_text("P3\n64 32\n255\n" + "\n".join(" ".join(str(v) for v in px) for row in rows for px in row) + "\n")
+    out = str(tmp_path / "mini_sky.ppm")
+    subprocess.check_call([exe, "--scene", "sky", "--obj", os.path.join(MINI, "mini.obj"), "--mtl", os.path.join(MINI, "mini.mtl"),
+                           "--width", "160", "--spp", "16", "--bounces", "6", "--ao", "0", "--vfov", "45", "--sky-image", str(sky_ppm),
+                           "--origin", "2.2,1.6,3.0", "--target", "0.0,0.5,0.0", "--out", out], stdout=subprocess.DEVNULL)
+    img_sky, w, h = read_ppm(out)
+    rt.scene_set(sky_sc)
+    assert np.array_equal(img_sky, rt.render(S.params_for(sky_sc))["canva"]) and not np.array_equal(img_sky, img)
     # failure is reported, not a crash: missing texture
     bad = subprocess.run([exe, "--scene", "sky", "--obj", os.path.join(MINI, "mini.obj"), "--mtl", "/nonexistent.mtl"], capture_output=True, text=True)
     assert bad.returncode == 1 and "cannot open" in bad.stderr

@@ -156,6 +156,21 @@ def test_render_c4_tree_same_stream(rt, oracle):
     _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
 
 
+def test_render_c4_sky_texture_same_stream(rt, oracle):
+    """Sky environment lookup (trt_sky_set; sphere_uvmapping, texture.h:92-112 + main.c:64-71): FP32 lat-long lookup on a
+    sphere of radius 1e5 against the FP64 oracle, same Philox stream; and switching it off restores the plain image."""
+    sc = S.tree_mesh_sky()
+    rp = S.params_for(sc, width=160, spp=8)
+    g, o = _compare_same_stream(rt, oracle, sc, rp, 0.95, 0.6)
+    assert len(np.unique(g["canva"], axis=0)) > 200          # the gradient + sun are visible, not one flat colour
+    plain = S.tree_mesh()
+    rt.scene_set(plain)                                       # scene without sky => trt_sky_set(NULL)
+    g2 = rt.render(rp)
+    o2 = oracle.render(plain, rp, rng=RNG_PHILOX)
+    assert (np.abs(g2["canva"] - o2["canva"]).max(axis=1) <= 1).mean() >= 0.95
+    assert not np.array_equal(g["canva"], g2["canva"])
+
+
 def test_render_c3b_pyramide_eau_same_stream(rt, oracle):
     """The scene main.c ships configured for: light / glass / water overrides, 20 bounces, coordinates up to 1800
     (FP32 ulp there is 1e-4, a thousand times the reference's 1e-7 triangle threshold)."""

@@ -28,7 +28,7 @@ ACCUM_CHANNELS, ACCUM_FRAC_BITS = 9, 28
 # every symbol include/tipe_rt.h declares
 ABI_SYMBOLS = [
     "trt_default_overrides", "trt_init", "trt_destroy", "trt_last_error", "trt_version",
-    "trt_scene_set", "trt_render", "trt_primary", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr",
+    "trt_scene_set", "trt_sky_set", "trt_render", "trt_primary", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr",
     "trt_stream", "trt_synchronize", "trt_bvh_info_get", "trt_debug_schedule",
     "trt_kat_hit_sphere", "trt_kat_hit_triangle", "trt_kat_refract", "trt_kat_philox", "trt_kat_tonemap",
 ]
@@ -158,6 +158,12 @@ class Renderer:
                                     _ptr(mats), C.c_int(sc.tex_w), C.c_int(sc.tex_h), C.c_int(sc.nb_materials),
                                     _ptr(quel), _ptr(ov), C.c_int(n_ov))
         self._check(rc, "trt_scene_set")
+        if sc.sky_mat_list is not None:
+            sky = np.ascontiguousarray(sc.sky_mat_list)
+            assert sky.shape[0] == sc.sky_w * sc.sky_h
+            self._check(self.lib.trt_sky_set(self.ctx, _ptr(sky), C.c_int(sc.sky_w), C.c_int(sc.sky_h)), "trt_sky_set")
+        else:
+            self._check(self.lib.trt_sky_set(self.ctx, None, C.c_int(0), C.c_int(0)), "trt_sky_set")
         self._scene = sc
 
     def bvh_info(self) -> dict:
@@ -192,9 +198,11 @@ class Renderer:
         self._check(self.lib.trt_accumulate(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), C.byref(st)), "trt_accumulate")
         return st.as_dict()
 
-    def resolve(self, rp: RenderParams, d_accum_ptr: int) -> dict:
+    def resolve(self, rp: RenderParams, d_accum_ptr: int, out: Optional[dict] = None) -> dict:
         n = rp.width * rp.height
-        canva, albedo, normal = np.empty((n, 3)), np.empty((n, 3)), np.empty((n, 3))
+        canva = out["canva"] if out else np.empty((n, 3))
+        albedo = out["albedo"] if out else np.empty((n, 3))
+        normal = out["normal"] if out else np.empty((n, 3))
         p = make_params(rp)
         self._check(self.lib.trt_resolve(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), _ptr(canva), _ptr(albedo), _ptr(normal)), "trt_resolve")
         return dict(canva=canva, albedo=albedo, normal=normal)

@@ -39,7 +39,7 @@ struct DeviceCtx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     // scene: grow-only device buffers, reused by every trt_scene_set (no cudaMalloc/cudaFree churn per frame)
-    Buf sph_raw, tri_raw, quel_mat, sph, sph_mat, tri, tri_uv, tri_orig, nodes, texels, mats_raw, ov_raw, scratch;
+    Buf sph_raw, tri_raw, quel_mat, sph, sph_mat, tri, tri_uv, tri_orig, nodes, texels, mats_raw, ov_raw, scratch, sky;
     DevScene scene{};
     // work buffers
     unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
@@ -294,6 +294,7 @@ TRT_API void trt_destroy(trt_ctx* ctx)
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         free_scene(d);
+        d.sky.release();
         if (d.accum) cudaFree(d.accum);
         if (d.wf_buf) cudaFree(d.wf_buf);
         if (d.out) cudaFree(d.out);
@@ -395,6 +396,28 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
     }
     ctx->info.ms_build = now_ms() - t0;
     ctx->has_scene = true;
+    return TRT_OK;
+}
+
+TRT_API int trt_sky_set(trt_ctx* ctx, const trt_material* sky_mat_list, int sky_width, int sky_height)
+{
+    if (!ctx) return TRT_ERR_INVALID;
+    if (sky_mat_list && (sky_width < 1 || sky_height < 1 || (long long)sky_width * sky_height > (1LL << 30)))
+        return fail(ctx, TRT_ERR_INVALID, "bad sky size %d x %d", sky_width, sky_height);
+    const size_t n = sky_mat_list ? (size_t)sky_width * (size_t)sky_height : 0;
+    std::vector<float4> rgb(n);
+    for (size_t k = 0; k < n; k++)
+        rgb[k] = make_float4((float)sky_mat_list[k].diffuseColor.e[0], (float)sky_mat_list[k].diffuseColor.e[1],
+                             (float)sky_mat_list[k].diffuseColor.e[2], 0.0f);
+    for (auto& d : ctx->devs) {
+        CU(ctx, cudaSetDevice(d.dev));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        if (n == 0) { d.scene.sky = nullptr; d.scene.sky_w = d.scene.sky_h = 0; continue; }
+        CU(ctx, d.sky.ensure(sizeof(float4) * n));
+        CU(ctx, cudaMemcpyAsync(d.sky.p, rgb.data(), sizeof(float4) * n, cudaMemcpyHostToDevice, d.stream));
+        CU(ctx, cudaStreamSynchronize(d.stream));
+        d.scene.sky = (const float4*)d.sky.p; d.scene.sky_w = sky_width; d.scene.sky_h = sky_height;
+    }
     return TRT_OK;
 }
 

@@ -41,6 +41,9 @@ struct DevScene {
     const float4* texels;
     int tex_w, tex_h, n_materials;
     float tri_tmin;             // FP32 stand-in for the 1e-7 distance threshold of mesh.h:88
+    // sky environment (trt_sky_set; nullptr = off): lat-long image, (r, g, b, 0) per texel, row 0 = bottom PPM row
+    const float4* sky;
+    int sky_w, sky_h;
 };
 // material record (sphere or texel), 3 x float4:
 //   [0] diffuse.rgb, alpha   [1] emission.rgb, emissionStrength   [2] reflectionStrength, materialIndex, 0, 0

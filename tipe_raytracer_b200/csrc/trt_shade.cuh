@@ -91,6 +91,19 @@ __device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* _
             const float4 cr = sph[hit_prim];
             n = normalize3(hp - xyz(cr));                                    // sphere.h:33 (always outward)
             m = unpack_material(sph_mat[3 * hit_prim], sph_mat[3 * hit_prim + 1], sph_mat[3 * hit_prim + 2]);
+            if (sc.sky != nullptr && hit_prim == sc.n_spheres - 1) {
+                // "cas du ciel" (main.c:64-71, commented out upstream) + sphere_uvmapping (texture.h:92-112): the last
+                // sphere emits the lat-long sky texel under the hit point and is opaque.  Index clamped like the oracle's.
+                const float inv_r = 1.0f / cr.w;
+                const float dx = (hp.x - cr.x) * inv_r, dy = (hp.y - cr.y) * inv_r, dz = (hp.z - cr.z) * inv_r;
+                const float theta = acosf(fminf(fmaxf(-dy, -1.0f), 1.0f));
+                const float phi = atan2f(-dz, dx) + 3.14159265358979f;
+                const int x = (int)(phi * 0.159154943091895f * (float)sc.sky_w);
+                const int y = (int)(theta * 0.318309886183791f * (float)sc.sky_h);
+                const int idx = min(max(y * sc.sky_w + x, 0), sc.sky_w * sc.sky_h - 1);
+                m.emission = xyz(__ldg(sc.sky + idx));
+                m.alpha = 1.0f;
+            }
         } else {
             const int leaf = hit_prim - sc.n_spheres;
             const float4 r2 = __ldg(sc.tri + 4 * leaf + 2);

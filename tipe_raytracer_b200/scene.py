@@ -119,6 +119,11 @@ class Scene:
     nb_materials: int = 0
     quel_mat_pour_tri: np.ndarray = dataclasses.field(default_factory=lambda: np.zeros(0, np.int32))
     overrides: Optional[np.ndarray] = None   # None => reference built-ins (texture.h:71-87)
+    # sky environment (ThreadData.sky_mat_list / sky_width / sky_height, main.c:29,34): MATERIAL[sky_h*sky_w] as
+    # create_mat_list loads it (texture.h:145-173), row 0 = bottom PPM row.  None => lookup off, like main.c:64-71 as shipped
+    sky_mat_list: Optional[np.ndarray] = None
+    sky_w: int = 0
+    sky_h: int = 0
     # default view / knobs of the config (main.c:293-317)
     cam_origin: tuple = (0.0, 0.0, 0.0)
     cam_target: tuple = (0.0, 0.0, -1.0)
@@ -302,6 +307,32 @@ def pyramide_eau(fixture: Optional[str] = None) -> Scene:
                  ratio=16.0 / 10.0, width=1000, spp=100, bounces=20, use_ao=False)
 
 
+def procedural_sky(w: int = 256, h: int = 128) -> np.ndarray:
+    """A synthetic lat-long sky in create_mat_list's layout (the reference's model3D/hdr/*.ppm are stripped from the mount):
+    horizon-to-zenith gradient, a warm sun disc and a dark ground half, quantised to 8 bits like a P3 PPM."""
+    v = (np.arange(h) + 0.5) / h                 # texture row y <-> theta = v*pi measured from -Y (texture.h:97,101): row 0 = straight down
+    u = (np.arange(w) + 0.5) / w
+    uu, vv = np.meshgrid(u, v)
+    up = np.clip((vv - 0.5) * 2.0, 0.0, 1.0)[..., None]
+    horizon = np.array([0.95, 0.85, 0.70]); zenith = np.array([0.25, 0.45, 0.95]); ground = np.array([0.18, 0.15, 0.12])
+    img = np.where(vv[..., None] >= 0.5, horizon * (1 - up) + zenith * up, ground)
+    sun = np.exp(-(((uu - 0.3) * 2.0) ** 2 + ((vv - 0.72) * 1.0) ** 2) / 0.0008)[..., None]
+    img = np.clip(img + sun * np.array([1.0, 0.9, 0.6]), 0.0, 1.0)
+    img = np.floor(img * 255.0) / 255.0
+    mats = np.zeros(w * h, MATERIAL)
+    mats["diffuseColor"] = img.reshape(-1, 3)
+    return mats
+
+
+def tree_mesh_sky(fixture: Optional[str] = None) -> Scene:
+    """C4 with the sky lookup switched on ("BVH + sky" taken literally): the tree under a lat-long sky image."""
+    sc = tree_mesh(fixture)
+    sc.name = "tree_mesh_sky_texture"
+    sc.sky_w, sc.sky_h = 256, 128
+    sc.sky_mat_list = procedural_sky(sc.sky_w, sc.sky_h)
+    return sc
+
+
 CONFIGS = {
     "C1": cornell_spheres,
     "C2": nature_mesh,
@@ -309,4 +340,5 @@ CONFIGS = {
     "C4": tree_mesh,
     "C5": readme_benchmark,
     "C3b": pyramide_eau,
+    "C4sky": tree_mesh_sky,
 }

@@ -244,10 +244,25 @@ def golden_leaves(ref: Ref):
     print("leaves: written")
 
 
+def golden_sky(ref):
+    """sphere_uvmapping (texture.h:92-112): hit points on a sphere -> the sky texel the reference reads."""
+    rng = np.random.default_rng(77)
+    out = {}
+    center = np.array([0.5, -2.0, 3.0]); radius = 100000.0; w, h = 256, 128
+    d = rng.normal(size=(512, 3)); d /= np.linalg.norm(d, axis=1)[:, None]
+    d[:6] = [[1, 0, 0], [-1, 1e-9, 1e-9], [0, 0, 1], [0, 0, -1], [0, 0.999999, 0.001], [0.001, -0.999, 0.001]]
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    pts = center + radius * d
+    out["center"], out["radius"], out["size"], out["points"] = center, np.float64(radius), np.array([w, h]), pts
+    out["index"] = np.array([ref.sphere_uvmapping(center, radius, p, w, h) for p in pts], np.int64)
+    np.savez_compressed(os.path.join(GOLDEN, "golden_sky.npz"), **out)
+    print("sky: written", out["index"][:8])
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     ref = Ref()
-    what = sys.argv[1:] or ["scenes", "primary", "renders", "leaves"]
+    what = sys.argv[1:] or ["scenes", "primary", "renders", "leaves", "sky"]
     if "scenes" in what:
         make_scenes(ref)
     if "primary" in what:
@@ -256,6 +271,8 @@ def main():
         golden_renders(ref)
     if "leaves" in what:
         golden_leaves(ref)
+    if "sky" in what:
+        golden_sky(ref)
 
 
 if __name__ == "__main__":
