@@ -188,12 +188,20 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             const float3 idir = safe_inverse(rd);
             const float3 ood = f3(P.o.x * idir.x, P.o.y * idir.y, P.o.z * idir.z);
             const int src_leaf = P.src_prim - sc.n_spheres, twin_leaf = P.src_twin;
-            const int exit_below = (A.exit_num * __popc(live_mask) + 31) >> 5;
+            const int n_live = __popc(live_mask);
+            const int exit_below = (A.exit_num * n_live + 31) >> 5;
+            int waste = 0;                          // idle lane-trips of this session (exit_waste policy)
             for (int step = 0;; step++) {
                 const bool inside = tr.node != TRT_TRAV_DONE || pend != 0;
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
-                if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
+                const int n_in = __popc(in_mask);
+                if (A.exit_waste > 0) {
+                    // "ski rental": a housekeeping pass costs about as much as 6-7 trips whatever the number of lanes it
+                    // serves, so leave once the lanes that are waiting for it have idled through exit_waste lane-trips
+                    if (step >= A.min_steps && waste >= A.exit_waste) break;
+                    waste += n_live - n_in;
+                } else if (step >= A.min_steps && n_in < exit_below) break;
                 if (COUNT) {
                     if (step == 0) sc_sessions++;
                     sc_trips++; sc_inside += __popc(in_mask);

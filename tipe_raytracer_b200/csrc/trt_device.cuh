@@ -41,6 +41,7 @@ struct DevScene {
     const float4* texels;
     int tex_w, tex_h, n_materials;
     float tri_tmin;             // FP32 stand-in for the 1e-7 distance threshold of mesh.h:88
+    float box_tmin;             // start of the ray interval in the slab tests: tri_tmin (a box the ray leaves before that cannot hold an accepted hit) or 0
     // sky environment (trt_sky_set; nullptr = off): lat-long image, (r, g, b, 0) per texel, row 0 = bottom PPM row
     const float4* sky;
     int sky_w, sky_h;

@@ -128,7 +128,7 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
         const float ax = (sc.root_lo.x - o.x) * idir.x, bx = (sc.root_hi.x - o.x) * idir.x;
         const float ay = (sc.root_lo.y - o.y) * idir.y, by = (sc.root_hi.y - o.y) * idir.y;
         const float az = (sc.root_lo.z - o.z) * idir.z, bz = (sc.root_hi.z - o.z) * idir.z;
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));
         if (COUNT) cnt.box_tests += 1;
         if (!(tf >= tn)) return;
@@ -210,7 +210,7 @@ __device__ __forceinline__ void bvh_visit(const DevScene& sc, float3 idir, float
         const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
         const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
         const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));           \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));           \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
         KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
     }
@@ -282,7 +282,7 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
         const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
         const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
         const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));           \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));           \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
         KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
     }
@@ -367,7 +367,7 @@ __device__ __forceinline__ void bvh_step_dual(const DevScene& sc, float3 o, floa
         const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
         const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
         const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));           \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));           \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
         KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
     }
