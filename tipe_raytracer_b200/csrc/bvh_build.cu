@@ -256,8 +256,11 @@ __device__ __forceinline__ float half_area(float4 lo, float4 hi)
 
 // ---- PLOC ----------------------------------------------------------------------------------------------
 // Clusters live in Morton order in (cid, clo, chi): cid < 0 is leaf ~p, cid >= 0 an internal node.
-__global__ void ploc_nearest(int c, const float4* __restrict__ clo, const float4* __restrict__ chi, int radius, int* nn)
+// The cluster count lives on the device (d_c): several passes are launched back to back without a host round trip,
+// each with a grid for the last count the host saw; threads beyond the current count leave at once.
+__global__ void ploc_nearest(const int* __restrict__ d_c, const float4* __restrict__ clo, const float4* __restrict__ chi, int radius, int* nn)
 {
+    const int c = *d_c;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     const float4 lo = clo[i], hi = chi[i];
@@ -274,11 +277,12 @@ __global__ void ploc_nearest(int c, const float4* __restrict__ clo, const float4
 }
 
 // Mutual nearest neighbours merge into a new internal node (owned by the lower index); flag[i] = cluster i survives.
-__global__ void ploc_merge(int c, int* cid, float4* clo, float4* chi, const int* __restrict__ nn, int* node_counter,
+__global__ void ploc_merge(const int* __restrict__ d_c, int c_bound, int* cid, float4* clo, float4* chi, const int* __restrict__ nn, int* node_counter,
                            int2* children, float4* node_lo, float4* node_hi, int* flag)
 {
+    const int c = *d_c;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c) return;
+    if (i >= c) { if (i < c_bound) flag[i] = 0; return; }       // the scan runs over c_bound entries
     const int j = nn[i];
     int keep = 1;
     if (j >= 0 && nn[j] == i) {
@@ -295,11 +299,14 @@ __global__ void ploc_merge(int c, int* cid, float4* clo, float4* chi, const int*
     flag[i] = keep;
 }
 
-__global__ void ploc_compact(int c, const int* __restrict__ cid, const float4* __restrict__ clo, const float4* __restrict__ chi,
+__global__ void ploc_compact(const int* __restrict__ d_c, int* d_c_next, const int* __restrict__ cid, const float4* __restrict__ clo, const float4* __restrict__ chi,
                              const int* __restrict__ flag, const int* __restrict__ pos, int* cid2, float4* clo2, float4* chi2)
 {
+    const int c = *d_c;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= c || !flag[i]) return;
+    if (i >= c) return;
+    if (i == c - 1) *d_c_next = pos[i] + flag[i];              // survivors = count of the next pass
+    if (!flag[i]) return;
     const int q = pos[i];
     cid2[q] = cid[i]; clo2[q] = clo[i]; chi2[q] = chi[i];
 }
@@ -492,20 +499,29 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
             const int radius = rad && *rad ? atoi(rad) : 64;
             BT(cudaMemsetAsync(node_counter, 0, sizeof(int), stream));
             ploc_init<<<grid_n, TB, 0, stream>>>(n, leaf_lo, leaf_hi, cid[0], clo[0], chi[0]);
-            int c = n, cur = 0, h_last[2];
-            for (int iter = 0; c > 1; iter++) {
-                const int g = (c + TB - 1) / TB;
-                ploc_nearest<<<g, TB, 0, stream>>>(c, clo[cur], chi[cur], radius, nn);
-                ploc_merge<<<g, TB, 0, stream>>>(c, cid[cur], clo[cur], chi[cur], nn, node_counter, children, node_lo, node_hi, flag);
-                { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, flag, pos, c, stream)); }
-                ploc_compact<<<g, TB, 0, stream>>>(c, cid[cur], clo[cur], chi[cur], flag, pos, cid[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1]);
+            // counts ping-pong between small[28] and small[29]; PLOC_BATCH passes per host read-back (a pass on a single
+            // cluster copies it across unchanged, so overshooting the end is harmless)
+            int* d_cnt = small + 28;
+            int c = n, cur = 0, passes = 0;
+            BT(cudaMemcpyAsync(d_cnt, &c, sizeof(int), cudaMemcpyHostToDevice, stream));
+            const int PLOC_BATCH = 8;
+            while (c > 1) {
+                const int c_bound = c;
+                const int g = (c_bound + TB - 1) / TB;
+                for (int b = 0; b < PLOC_BATCH; b++, passes++) {
+                    const int* d_c = d_cnt + (passes & 1); int* d_c_next = d_cnt + ((passes + 1) & 1);
+                    ploc_nearest<<<g, TB, 0, stream>>>(d_c, clo[cur], chi[cur], radius, nn);
+                    ploc_merge<<<g, TB, 0, stream>>>(d_c, c_bound, cid[cur], clo[cur], chi[cur], nn, node_counter, children, node_lo, node_hi, flag);
+                    { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, flag, pos, c_bound, stream)); }
+                    ploc_compact<<<g, TB, 0, stream>>>(d_c, d_c_next, cid[cur], clo[cur], chi[cur], flag, pos, cid[cur ^ 1], clo[cur ^ 1], chi[cur ^ 1]);
+                    cur ^= 1;
+                }
                 BT(cudaGetLastError());
-                BT(cudaMemcpyAsync(h_last, pos + c - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-                BT(cudaMemcpyAsync(h_last + 1, flag + c - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+                int c_new = 0;
+                BT(cudaMemcpyAsync(&c_new, d_cnt + (passes & 1), sizeof(int), cudaMemcpyDeviceToHost, stream));
                 BT(cudaStreamSynchronize(stream));
-                const int c_new = h_last[0] + h_last[1];
-                if (c_new >= c || c_new < 1 || iter > 4096) return cudaErrorUnknown;     // every pass merges at least one pair
-                c = c_new; cur ^= 1;
+                if (c_new >= c || c_new < 1 || passes > 8192) return cudaErrorUnknown;     // every pass on > 1 clusters merges at least one pair
+                c = c_new;
             }
             BT(cudaMemcpyAsync(&root, cid[cur], sizeof(int), cudaMemcpyDeviceToHost, stream));
             BT(cudaStreamSynchronize(stream));
