@@ -39,9 +39,9 @@ __device__ __forceinline__ void decode_item(const RenderArgs& A, long long item,
     else { chunk = local % A.n_chunks; p = local / A.n_chunks; }
 }
 
-// fill_canva's per-sample set-up (main.c:265-271) + get_ray (camera.h:42-54).
+// fill_canva's per-sample set-up (main.c:265-271) + get_ray (camera.h:42-54): the primary ray of (pixel, sample).
 // A.cam_corner = coin_bas_gauche - origin, formed in FP64 on the host.
-__device__ __forceinline__ void start_path(const RenderArgs& A, int pixel, int px, int py, int sample, PathState& P)
+__device__ __forceinline__ void camera_ray(const RenderArgs& A, int pixel, int px, int py, int sample, float3& o, float3& d)
 {
     const uint4 r = philox4x32_10((uint32_t)pixel, (uint32_t)(A.sample_offset + sample), 0u, 0u, A.key0, A.key1);
     const float u = ((float)px + (u01(r.x) - 0.5f)) * A.inv_wm1;
@@ -50,13 +50,24 @@ __device__ __forceinline__ void start_path(const RenderArgs& A, int pixel, int p
     const float dy = (u01(r.w) - 0.5f) * A.aperture_y;
     const float3 direction = fma3(A.cam_hor, u, fma3(A.cam_ver, v, A.cam_corner));
     const float3 dest = fma3(direction, A.focus, A.cam_origin);
-    P.o = f3(A.cam_origin.x + dx, A.cam_origin.y + dy, A.cam_origin.z);
-    P.d = normalize3(dest - P.o);
+    o = f3(A.cam_origin.x + dx, A.cam_origin.y + dy, A.cam_origin.z);
+    d = normalize3(dest - o);
+}
+
+// tracer()'s locals at entry (main.c:119-130)
+__device__ __forceinline__ void init_path_state(PathState& P)
+{
     P.T = f3(1, 1, 1); P.L = f3(0, 0, 0);
     P.aov_albedo = P.aov_normal = f3(0, 0, 0);
     P.cur_index = 1.0f; P.bounce = 0; P.alpha_depth = 0; P.is_alpha = false;
     P.src_prim = TRT_NO_PRIM; P.src_twin = -1;
     P.ao_pending = false;
+}
+
+__device__ __forceinline__ void start_path(const RenderArgs& A, int pixel, int px, int py, int sample, PathState& P)
+{
+    camera_ray(A, pixel, px, py, sample, P.o, P.d);
+    init_path_state(P);
 }
 
 // One completed closest_hit query -> one trip of the bounce loop (main.c:132-239) or the end of an
