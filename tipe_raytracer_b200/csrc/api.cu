@@ -143,7 +143,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     // tuning knobs (defaults chosen from measurements on B200); env overrides are for experiments
     auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     const bool brute = (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, count_tests = (p->flags & TRT_FLAG_COUNT_TESTS) != 0;
-    // engine: triangles => wavefront (small high-occupancy query kernel), spheres only => register-resident megakernel
+    // engine 1 = register-resident megakernel (default), 2 = wavefront (opt-in, TRT_ENGINE=2)
     int engine = knob("TRT_ENGINE", 0);
     if (engine == 0) engine = 1;    // measured on B200: the megakernel wins on every reference scene; the wavefront engine is opt-in
     if (engine == 2 && (brute || p->nbRebondMax > 8191)) engine = 1;
@@ -152,7 +152,6 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 12);
     A.vote = knob("TRT_TUNE_VOTE", 0);
     A.max_hk = knob("TRT_TUNE_MAX_HK", 4);
-    A.exit_waste = knob("TRT_TUNE_WASTE", 0);
     A.item_order = knob("TRT_TUNE_ORDER", d.scene.n_tris > 0 ? 1 : 0);   // meshes: a warp starts on the samples of 2-3 neighbouring pixels (coherent primary rays, +2-3 %); spheres: one tile (+5 %)
     A.count_tests = count_tests ? 1 : 0;
     A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);

@@ -11,8 +11,8 @@
 //     lanes as they run dry, so lanes never wait for each other's paths ("ray regeneration"):
 //     every trip of the main loop traces exactly one ray per live lane — a bounce ray or an
 //     ambient-occlusion ray — whatever bounce or sample the lane is at;
-//   * a lane keeps the 9 sums of its item in registers as int64 fixed point and flushes them with
-//     9 RED.ADD.64 when the item ends: integer adds commute, so the image is bit-identical for any
+//   * a lane keeps the 9 sums of its item as int64 fixed point in shared memory (18 registers saved) and flushes them
+//     with 9 RED.ADD.64 when the item ends: integer adds commute, so the image is bit-identical for any
 //     schedule, any grid and any split of the samples over GPUs;
 //   * spheres (and their materials) are staged once per CTA into shared memory; BVH nodes,
 //     triangles and texels are read through the read-only path and live in L1/L2.
@@ -188,20 +188,12 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             const float3 idir = safe_inverse(rd);
             const float3 ood = f3(P.o.x * idir.x, P.o.y * idir.y, P.o.z * idir.z);
             const int src_leaf = P.src_prim - sc.n_spheres, twin_leaf = P.src_twin;
-            const int n_live = __popc(live_mask);
-            const int exit_below = (A.exit_num * n_live + 31) >> 5;
-            int waste = 0;                          // idle lane-trips of this session (exit_waste policy)
+            const int exit_below = (A.exit_num * __popc(live_mask) + 31) >> 5;
             for (int step = 0;; step++) {
                 const bool inside = tr.node != TRT_TRAV_DONE || pend != 0;
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
-                const int n_in = __popc(in_mask);
-                if (A.exit_waste > 0) {
-                    // "ski rental": a housekeeping pass costs about as much as 6-7 trips whatever the number of lanes it
-                    // serves, so leave once the lanes that are waiting for it have idled through exit_waste lane-trips
-                    if (step >= A.min_steps && waste >= A.exit_waste) break;
-                    waste += n_live - n_in;
-                } else if (step >= A.min_steps && n_in < exit_below) break;
+                if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
                 if (COUNT) {
                     if (step == 0) sc_sessions++;
                     sc_trips++; sc_inside += __popc(in_mask);

@@ -117,6 +117,13 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
                  : "l"(p));
 }
 
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 __device__ __forceinline__ unsigned lanemask_lt()
 {
     unsigned m;

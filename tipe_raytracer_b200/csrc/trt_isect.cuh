@@ -53,7 +53,7 @@ __device__ __forceinline__ bool triangle_test(float4 r0, float4 r1, float4 r2, f
     const float det = -dot3(d, N);
     const float3 ao = o - A;
     const float3 dao = cross3(ao, d);
-    const float inv = __frcp_rn(det);
+    const float inv = rcp_approx(det);              // MUFU.RCP, 1 ulp: the accepted-hit thresholds below are 1e-6 / 1e-7, far coarser
     t = dot3(ao, N) * inv;
     u = dot3(AC, dao) * inv;
     v = -dot3(AB, dao) * inv;
@@ -79,10 +79,11 @@ struct Trav {
 
 __device__ __forceinline__ float3 safe_inverse(float3 d)
 {
+    // MUFU.RCP (1 ulp): the slab tests only have to be conservative, and the boxes are padded by 2^-21 of the scene size
     const float e = 1e-30f;
-    return f3(1.0f / (fabsf(d.x) > e ? d.x : copysignf(e, d.x)),
-              1.0f / (fabsf(d.y) > e ? d.y : copysignf(e, d.y)),
-              1.0f / (fabsf(d.z) > e ? d.z : copysignf(e, d.z)));
+    return f3(rcp_approx(fabsf(d.x) > e ? d.x : copysignf(e, d.x)),
+              rcp_approx(fabsf(d.y) > e ? d.y : copysignf(e, d.y)),
+              rcp_approx(fabsf(d.z) > e ? d.z : copysignf(e, d.z)));
 }
 
 // any_hit: the caller only needs "hit anything" (ambient_occlusion, main.c:104-106).

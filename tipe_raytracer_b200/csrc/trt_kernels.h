@@ -26,7 +26,6 @@ struct RenderArgs {
     int chunk, n_chunks, tiles_x, tiles_y;
     int min_steps, exit_num, vote;      // BVH-loop policy, see pathtrace.cu (vote = 1: deferred leaves, bvh_trip)
     int max_hk;                         // megakernel: housekeeping passes per trip
-    int exit_waste;                     // megakernel: > 0 = leave the BVH loop after this many idle lane-trips (0 = exit_num threshold)
     int item_order;                     // see decode_item (trt_shade.cuh)
     int count_tests, wf_blocks, wf_check; // wavefront engine: count box/tri tests; trace CTAs per SM; waves between liveness checks
     long long n_items;
