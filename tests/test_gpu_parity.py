@@ -171,6 +171,34 @@ def test_render_c4_sky_texture_same_stream(rt, oracle):
     assert not np.array_equal(g["canva"], g2["canva"])
 
 
+def test_render_mesh_with_ambient_occlusion_same_stream(rt, oracle):
+    """AO rays against a BVH (any-hit traversal, alpha ignored: main.c:104-106) — what main.c does when useAO stays true with a mesh."""
+    sc = S.nature_mesh()
+    sc.use_ao = True
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    a = rt.render(S.params_for(sc, width=96, spp=4, flags=FLAG_BRUTE_FORCE))          # linear scan = BVH, AO included
+    b = rt.render(S.params_for(sc, width=96, spp=4))
+    assert np.array_equal(a["canva"], b["canva"]) and a["stats"]["rays"] == b["stats"]["rays"]
+
+
+def test_render_spheres_and_mesh_mixed_with_ao_same_stream(rt, oracle):
+    """The README box (10 spheres, mirror walls, lights) with the tree mesh inside it: closest_hit's sphere loop and
+    triangle loop compete (main.c:59-90), AO on, rays leave spheres and triangles alike."""
+    sc = S.tree_mesh()
+    box = S.cornell_spheres()
+    sc.spheres = box.spheres
+    sc.triangles = sc.triangles.copy()
+    for f in ("A", "B", "C"):
+        sc.triangles[f] = sc.triangles[f] * 0.6 + np.array([0.0, -0.4, -2.4])       # scaled into the box
+    sc.use_ao = True
+    sc.cam_origin, sc.cam_target, sc.vfov, sc.ratio = box.cam_origin, box.cam_target, box.vfov, box.ratio
+    rp = S.params_for(sc, width=128, spp=8, bounces=5)
+    g, o = _compare_same_stream(rt, oracle, sc, rp, 0.93, 0.8)
+    prim_g, prim_o = rt.primary(rp), oracle.primary(sc, rp)
+    assert np.array_equal(prim_g["id"], prim_o["id"])
+    assert (prim_g["id"] >= 10).mean() > 0.03 and (prim_g["id"] < 10).mean() > 0.5   # both kinds of primitive are seen
+
+
 def test_render_c3b_pyramide_eau_same_stream(rt, oracle):
     """The scene main.c ships configured for: light / glass / water overrides, 20 bounces, coordinates up to 1800
     (FP32 ulp there is 1e-4, a thousand times the reference's 1e-7 triangle threshold)."""
