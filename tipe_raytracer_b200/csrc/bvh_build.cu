@@ -9,6 +9,11 @@
 //   2. morton_keys     36-bit Morton code of the centroid << 28 | triangle index  (unique 64-bit keys)
 //   3. radix sort      cub::DeviceRadixSort (library; the build is not on the per-ray path)
 //   4. emit_leaves     triangles re-laid out in sorted (leaf) order: A, AB, AC, N + ids as 4 float4 (64 B)
+//   4b. group_heads    triangles with IDENTICAL boxes (the two halves of a quad, the back faces of a double-faced mesh, crossed
+//                      plant quads: 2, 4 or 8 triangles per box in the reference's Minecraft exports) are neighbours after
+//                      the sort and become ONE leaf: the hierarchy is built over the distinct boxes, and a leaf step tests
+//                      the whole run (count in the head record).  Without this the tree has to separate equal boxes with
+//                      inner nodes every ray through the box visits in full.
 //   5. find_twins      coincident opposite-facing triangles ("doubleface" meshes) share a Morton code and
 //                      are neighbours after the sort; each records the other's leaf position
 //   6. hierarchy       PLOC (Meister & Bittner 2018), the default: clusters in Morton order repeatedly merge with
@@ -120,7 +125,7 @@ __global__ void morton_keys(int n, const float4* __restrict__ box_lo, const floa
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const float4 lo = box_lo[k], hi = box_hi[k];
-    const float cx = lo.w, cy = hi.w, cz = 0.5f * (lo.z + hi.z);   // x,y centroid exact; z: box centre
+    const float cx = 0.5f * (lo.x + hi.x), cy = 0.5f * (lo.y + hi.y), cz = 0.5f * (lo.z + hi.z);   // box centre: equal boxes get equal codes
     float q[3];
     const float c[3] = {cx, cy, cz};
     for (int a = 0; a < 3; a++) {
@@ -153,6 +158,36 @@ __global__ void emit_leaves(int n, const unsigned long long* __restrict__ keys, 
     const float4 lo = box_lo[k], hi = box_hi[k];
     leaf_lo[p] = make_float4(lo.x - pad, lo.y - pad, lo.z - pad, 0.0f);
     leaf_hi[p] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, 0.0f);
+}
+
+// head[p] = 1 when the triangle at sorted position p starts a new box (group == 0: every triangle is its own leaf)
+__global__ void group_heads(int n, const unsigned long long* __restrict__ keys, const float4* __restrict__ box_lo,
+                            const float4* __restrict__ box_hi, int group, int* head)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int h = 1;
+    if (p > 0 && group) {
+        const int k = (int)(keys[p] & IDX_MASK), q = (int)(keys[p - 1] & IDX_MASK);
+        const float4 a = box_lo[k], b = box_hi[k], c = box_lo[q], d = box_hi[q];
+        h = !(a.x == c.x && a.y == c.y && a.z == c.z && b.x == d.x && b.y == d.y && b.z == d.z);
+    }
+    head[p] = h;
+}
+
+__global__ void group_first(int n, const int* __restrict__ head, const int* __restrict__ gpos, int* gfirst)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n && head[p]) gfirst[gpos[p]] = p;
+}
+
+// the head record of every leaf carries the number of triangles of the run
+__global__ void group_counts(int n_groups, int n, const int* __restrict__ gfirst, float4* tri)
+{
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int first = gfirst[g], next = (g + 1 < n_groups) ? gfirst[g + 1] : n;
+    tri[4 * first + 3].w = __int_as_float(next - first);
 }
 
 __device__ __forceinline__ bool same_point(const double* a, const double* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
@@ -311,11 +346,13 @@ __global__ void ploc_compact(const int* __restrict__ d_c, int* d_c_next, const i
     cid2[q] = cid[i]; clo2[q] = clo[i]; chi2[q] = chi[i];
 }
 
-__global__ void ploc_init(int n, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int* cid, float4* clo, float4* chi)
+__global__ void ploc_init(int n_groups, const int* __restrict__ gfirst, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                          int* cid, float4* clo, float4* chi)
 {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    cid[p] = ~p; clo[p] = leaf_lo[p]; chi[p] = leaf_hi[p];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const int p = gfirst[g];                 // a leaf is referenced by the position of its first triangle
+    cid[g] = ~p; clo[g] = leaf_lo[p]; chi[g] = leaf_hi[p];
 }
 
 __global__ void sah_cost_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
@@ -398,13 +435,13 @@ size_t trt_build_scratch_bytes(int n_tris)
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, n_tris, 0);
     if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
     const size_t n = (size_t)n_tris;
-    return 8 * align256(sizeof(float4) * n) + 2 * align256(8 * n) + 3 * align256(sizeof(int2) * n) + 3 * align256(sizeof(int) * n) + 256 + align256(cub_bytes) + 4096;
+    return 8 * align256(sizeof(float4) * n) + 2 * align256(8 * n) + 3 * align256(sizeof(int2) * n) + 6 * align256(sizeof(int) * n) + 256 + align256(cub_bytes) + 4096;
 }
 
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream)
 {
     out.root = 0; out.max_depth = 0; out.n_twins = 0; out.sah_cost = 0.0; out.tri_tmin = 1e-7f;
-    out.n_wide_nodes = 0; out.wide_depth = 0; out.binary_depth = 0;
+    out.n_wide_nodes = 0; out.wide_depth = 0; out.binary_depth = 0; out.n_groups = 0;
     out.root_lo = make_float3(0, 0, 0); out.root_hi = make_float3(0, 0, 0);
     const int TB = 256;
 
@@ -436,6 +473,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     const size_t o_keys_a = take(sizeof(unsigned long long) * n), o_keys_b = take(sizeof(unsigned long long) * n);
     const size_t o_children = take(sizeof(int2) * n), o_parent_node = take(sizeof(int) * n), o_parent_leaf = take(sizeof(int) * n);
     const size_t o_flags = take(sizeof(int) * n);
+    const size_t o_ghead = take(sizeof(int) * n), o_gpos = take(sizeof(int) * n), o_gfirst = take(sizeof(int) * n);
     const size_t o_queue_a = take(sizeof(int2) * n), o_queue_b = take(sizeof(int2) * n);
     const size_t o_c1lo = take(sizeof(float4) * n), o_c1hi = take(sizeof(float4) * n);     // PLOC ping-pong cluster boxes
     const size_t o_small = take(256);                 // bounds[7], max_depth, n_twins, sah (double at +64), collapse counters, PLOC node counter
@@ -450,6 +488,11 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     int *parent_node = (int*)(base + o_parent_node), *parent_leaf = (int*)(base + o_parent_leaf), *flags = (int*)(base + o_flags);
     int* small = (int*)(base + o_small);
     double* sah = (double*)(base + o_small + 64);
+    int *ghead = (int*)(base + o_ghead), *gpos = (int*)(base + o_gpos), *gfirst = (int*)(base + o_gfirst);
+    const char* bvh_mode = getenv("TRT_BVH");
+    const bool lbvh = bvh_mode && strcmp(bvh_mode, "lbvh") == 0;
+    const char* grp = getenv("TRT_TUNE_GROUP");
+    const int group = (!lbvh && !(grp && *grp && atoi(grp) == 0)) ? 1 : 0;       // equal-box runs become one leaf (PLOC only)
 
     // bounds init: min = +big, max = -big in ordered-int space
     int h_small[64];
@@ -465,10 +508,19 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     BT(cudaGetLastError());
     BT(cub::DeviceRadixSort::SortKeys(base + o_cub, cub_bytes, keys_a, keys_b, n, 0, 64, stream));
 
+    group_heads<<<grid_n, TB, 0, stream>>>(n, keys_b, box_lo, box_hi, group, ghead);
+    { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, ghead, gpos, n, stream)); }
+    group_first<<<grid_n, TB, 0, stream>>>(n, ghead, gpos, gfirst);
+    BT(cudaGetLastError());
+
     // scene scale -> box padding and the FP32 distance threshold
-    int h_bounds[8];
+    int h_bounds[8], h_grp[2];
     BT(cudaMemcpyAsync(h_bounds, small, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
+    BT(cudaMemcpyAsync(h_grp, gpos + n - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    BT(cudaMemcpyAsync(h_grp + 1, ghead + n - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
     BT(cudaStreamSynchronize(stream));
+    const int n_groups = h_grp[0] + h_grp[1];
+    if (n_groups < 1 || n_groups > n) return cudaErrorUnknown;
     auto ord2f_h = [](int i) { int b = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &b, 4); return f; };
     const float amax = ord2f_h(h_bounds[6]);
     const float pad = amax * 4.76837158e-7f + 1e-30f;                    // 2^-21 relative
@@ -479,13 +531,14 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     emit_leaves<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, in.quel_mat, box_lo, box_hi, pad,
                                           out.tri, out.tri_uv, out.tri_orig, leaf_lo, leaf_hi);
     find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, out.tri, small + 9);
+    group_counts<<<(n_groups + TB - 1) / TB, TB, 0, stream>>>(n_groups, n, gfirst, out.tri);
     BT(cudaGetLastError());
-    if (n == 1) {
+    out.n_groups = n_groups;
+    if (n_groups == 1) {
         out.root = ~0; out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;
     } else {
         int root = 0;
-        const char* mode = getenv("TRT_BVH");
-        if (mode && strcmp(mode, "lbvh") == 0) {
+        if (lbvh) {
             build_hierarchy<<<grid_n, TB, 0, stream>>>(n, keys_b, children, parent_node, parent_leaf);
             refit<<<grid_n, TB, 0, stream>>>(n, children, parent_node, parent_leaf, leaf_lo, leaf_hi, node_lo, node_hi, flags, small + 8);
         } else {
@@ -498,11 +551,11 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
             const char* rad = getenv("TRT_TUNE_PLOC_RADIUS");
             const int radius = rad && *rad ? atoi(rad) : 64;
             BT(cudaMemsetAsync(node_counter, 0, sizeof(int), stream));
-            ploc_init<<<grid_n, TB, 0, stream>>>(n, leaf_lo, leaf_hi, cid[0], clo[0], chi[0]);
+            ploc_init<<<(n_groups + TB - 1) / TB, TB, 0, stream>>>(n_groups, gfirst, leaf_lo, leaf_hi, cid[0], clo[0], chi[0]);
             // counts ping-pong between small[28] and small[29]; PLOC_BATCH passes per host read-back (a pass on a single
             // cluster copies it across unchanged, so overshooting the end is harmless)
             int* d_cnt = small + 28;
-            int c = n, cur = 0, passes = 0;
+            int c = n_groups, cur = 0, passes = 0;
             BT(cudaMemcpyAsync(d_cnt, &c, sizeof(int), cudaMemcpyHostToDevice, stream));
             const int PLOC_BATCH = 8;
             while (c > 1) {
@@ -525,9 +578,9 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
             }
             BT(cudaMemcpyAsync(&root, cid[cur], sizeof(int), cudaMemcpyDeviceToHost, stream));
             BT(cudaStreamSynchronize(stream));
-            if (root < 0 || root >= n - 1) return cudaErrorUnknown;
+            if (root < 0 || root >= n_groups - 1) return cudaErrorUnknown;
         }
-        sah_cost_kernel<<<grid_n, TB, 0, stream>>>(n, children, leaf_lo, leaf_hi, node_lo, node_hi, root, sah);
+        sah_cost_kernel<<<grid_n, TB, 0, stream>>>(lbvh ? n : n_groups, children, leaf_lo, leaf_hi, node_lo, node_hi, root, sah);
         BT(cudaGetLastError());
         // binary -> 4-wide, one launch per level (the queue sizes come back to the host: ~depth/2 round trips)
         int2* q[2] = {(int2*)(base + o_queue_a), (int2*)(base + o_queue_b)};
@@ -556,8 +609,8 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     BT(cudaMemcpyAsync(h_tail, small + 8, sizeof(int) * 2, cudaMemcpyDeviceToHost, stream));
     BT(cudaMemcpyAsync(&h_sah, sah, sizeof(double), cudaMemcpyDeviceToHost, stream));
     BT(cudaStreamSynchronize(stream));
-    if (n > 1) out.binary_depth = h_tail[0];
-    out.max_depth = n > 1 ? out.wide_depth + 1 : 1;
+    if (n_groups > 1) out.binary_depth = h_tail[0];
+    out.max_depth = n_groups > 1 ? out.wide_depth + 1 : 1;
     out.n_twins = h_tail[1];
     out.sah_cost = h_sah;
     return cudaSuccess;

@@ -27,7 +27,7 @@
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT>
 __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
@@ -60,8 +60,6 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     const bool fuse_ao = !HAS_TRIS && A.use_ao;      // sphere-only scenes: AO ray + next bounce ray in one scan
     Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
     int stack[TRT_STACK_DEPTH];
-    float stack_t[MODE == 3 ? TRT_STACK_DEPTH : 1];   // entry distances of the stacked children (MODE 3: culled at pop time)
-    int pend = 0;                           // parked leaf (0 = none), see bvh_trip / bvh_step_dual
 
     unsigned ray_count = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
@@ -78,11 +76,11 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         bool new_ray = false;
         if (COUNT) {
             sc_hk++;
-            sc_consume += __popc(__ballot_sync(0xffffffffu, tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)));
+            sc_consume += __popc(__ballot_sync(0xffffffffu, tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)));
         }
 
         // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
-        if (tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)) {
+        if (tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)) {
             PathResult res;
             if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res, fuse_ao)) {
                 my_acc[0 * PT_THREADS] += to_fixed(res.L.x);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z);
@@ -175,8 +173,8 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             }
         }
         if (!HAS_TRIS || BRUTE || hk + 1 >= A.max_hk) break;
-        const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE || pend != 0));
-        const int n_ready = __popc(__ballot_sync(0xffffffffu, phase != PH_DONE && tr.node == TRT_TRAV_DONE && pend == 0));
+        const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE));
+        const int n_ready = __popc(__ballot_sync(0xffffffffu, phase != PH_DONE && tr.node == TRT_TRAV_DONE));
         if (n_ready == 0 || n_inside >= ((A.exit_num * __popc(live_mask) + 31) >> 5)) break;
       }
       if (live_mask == 0) break;
@@ -190,7 +188,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             const int src_leaf = P.src_prim - sc.n_spheres, twin_leaf = P.src_twin;
             const int exit_below = (A.exit_num * __popc(live_mask) + 31) >> 5;
             for (int step = 0;; step++) {
-                const bool inside = tr.node != TRT_TRAV_DONE || pend != 0;
+                const bool inside = tr.node != TRT_TRAV_DONE;
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
                 if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
@@ -198,17 +196,11 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                     if (step == 0) sc_sessions++;
                     sc_trips++; sc_inside += __popc(in_mask);
                     sc_node += __popc(__ballot_sync(0xffffffffu, tr.node >= 0 && tr.node != TRT_TRAV_DONE));
-                    sc_leaf += __popc(__ballot_sync(0xffffffffu, MODE >= 1 ? pend != 0 : tr.node < 0));
+                    sc_leaf += __popc(__ballot_sync(0xffffffffu, tr.node < 0));
                 }
-                if (MODE == 1) {
-                    bvh_trip<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, inside, tr, pend, stack, cnt);
-                } else if (MODE >= 2) {
-                    // node visit + parked leaf test in the same trip
-                    if (inside) bvh_step_dual<COUNT, MODE == 3>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, pend, stack, stack_t, cnt);
-                } else {
-                    // if-if: every trip, each lane does whatever it is at (measured faster than deferral on B200)
-                    if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
-                }
+                // if-if: every trip, each lane does whatever it is at — a node visit or a leaf test (measured faster than
+                // deferring, voting on or pairing the two on B200, profiles/README.md)
+                if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
             }
         }
     }
@@ -290,10 +282,10 @@ cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, 
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, int MODE = 0>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
 {
-    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, MODE><<<grid, PT_THREADS, smem, stream>>>(A);
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 
@@ -306,19 +298,8 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
-    if (count_tests) {
-        switch (A.vote) {
-            case 2: return launch_variant<true, false, true, 2>(A, grid, smem, stream);
-            case 3: return launch_variant<true, false, true, 3>(A, grid, smem, stream);
-            default: return launch_variant<true, false, true, 0>(A, grid, smem, stream);
-        }
-    }
-    switch (A.vote) {
-        case 1: return launch_variant<true, false, false, 1>(A, grid, smem, stream);
-        case 2: return launch_variant<true, false, false, 2>(A, grid, smem, stream);
-        case 3: return launch_variant<true, false, false, 3>(A, grid, smem, stream);
-        default: return launch_variant<true, false, false, 0>(A, grid, smem, stream);
-    }
+    return count_tests ? launch_variant<true, false, true>(A, grid, smem, stream)
+                       : launch_variant<true, false, false>(A, grid, smem, stream);
 }
 
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream)

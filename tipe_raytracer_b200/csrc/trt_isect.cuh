@@ -65,8 +65,8 @@ __device__ __forceinline__ bool triangle_test(float4 r0, float4 r1, float4 r2, f
 // closest_hit (main.c:52-92): spheres in order, then triangles; strict '<' keeps the first primitive
 // on exact ties (for triangles: the lower index in the caller's array).
 // The query is split so that a warp can leave the BVH loop while some lanes are still inside it:
-//   ray_begin  : the sphere scan (uniform trip count, no divergence) + traversal set-up
-//   bvh_step   : one node visit or one leaf test; state lives in Trav + the lane's local stack
+//   ray_begin        : the sphere scan (uniform trip count, no divergence) + traversal set-up
+//   bvh_step_unified : one node visit or one leaf test; state lives in Trav + the lane's local stack
 #define TRT_TRAV_DONE 0x7fffffff
 
 struct Trav {
@@ -184,78 +184,13 @@ __device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* _
     if (COUNT) cnt.sphere_tests += ns * ((do_bounce ? 1 : 0) + (do_ao ? 1 : 0));
 }
 
-// One visit of a 4-wide node for a lane with tr.node >= 0 (and != TRT_TRAV_DONE): four slab tests,
-// children that are hit are ordered by entry distance (5-comparator network), the nearest is
-// visited next and the others pushed farthest first.
+// compare-exchange of (key, ref) pairs: the 5-comparator network below sorts the four children by entry distance
 __device__ __forceinline__ void order2(float& ka, int& ra, float& kb, int& rb)
 {
     const bool sw = kb < ka;
     const float k0 = sw ? kb : ka, k1 = sw ? ka : kb;
     const int r0 = sw ? rb : ra, r1 = sw ? ra : rb;
     ka = k0; kb = k1; ra = r0; rb = r1;
-}
-
-template <bool COUNT>
-__device__ __forceinline__ void bvh_visit(const DevScene& sc, float3 idir, float3 ood, Trav& tr, int* stack, TraceCounters& cnt)
-{
-    const float4* nd = sc.nodes + 8 * (size_t)tr.node;
-    float4 lox, hix, loy, hiy, loz, hiz, chf, pad;
-    const int rot = tr.node & 3;                    // fields are stored rotated by the node index (bvh_build.cu)
-    ldg256(nd + 2 * ((0 + rot) & 3), lox, hix); ldg256(nd + 2 * ((1 + rot) & 3), loy, hiy);
-    ldg256(nd + 2 * ((2 + rot) & 3), loz, hiz); ldg256(nd + 2 * ((3 + rot) & 3), chf, pad);
-    const int4 ch = make_int4(__float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w));
-    if (COUNT) cnt.box_tests += 4;
-    const float INF = __int_as_float(0x7f800000);
-#define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
-    {                                                                                                      \
-        const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
-        const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
-        const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));           \
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
-        KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
-    }
-    float k0, k1, k2, k3;
-    int r0 = ch.x, r1 = ch.y, r2 = ch.z, r3 = ch.w;
-    TRT_SLAB(lox.x, hix.x, loy.x, hiy.x, loz.x, hiz.x, r0, k0)
-    TRT_SLAB(lox.y, hix.y, loy.y, hiy.y, loz.y, hiz.y, r1, k1)
-    TRT_SLAB(lox.z, hix.z, loy.z, hiy.z, loz.z, hiz.z, r2, k2)
-    TRT_SLAB(lox.w, hix.w, loy.w, hiy.w, loz.w, hiz.w, r3, k3)
-#undef TRT_SLAB
-    order2(k0, r0, k1, r1); order2(k2, r2, k3, r3);
-    order2(k0, r0, k2, r2); order2(k1, r1, k3, r3);
-    order2(k1, r1, k2, r2);
-    // k0 <= k1 <= k2 <= k3; misses carry +inf and sort last
-    int sp = tr.sp;
-    if (k3 < INF) stack[sp++] = r3;
-    if (k2 < INF) stack[sp++] = r2;
-    if (k1 < INF) stack[sp++] = r1;
-    if (k0 < INF) { tr.node = r0; tr.sp = sp; }
-    else { tr.node = stack[sp - 1]; tr.sp = sp - 1; }
-}
-
-// One leaf test for a lane with tr.node < 0: the triangle at leaf position ~node.
-template <bool COUNT>
-__device__ __forceinline__ void bvh_leaf(const DevScene& sc, float3 o, float3 d, int src_leaf, int twin_leaf, bool any_hit,
-                                         Trav& tr, int* stack, TraceCounters& cnt)
-{
-    const int p = ~tr.node;
-    int next = stack[--tr.sp];
-    if (p != src_leaf && p != twin_leaf) {
-        float t, u, v;
-        const float4 r0 = __ldg(sc.tri + 4 * p), r1 = __ldg(sc.tri + 4 * p + 1), r2 = __ldg(sc.tri + 4 * p + 2);
-        if (COUNT) cnt.tri_tests++;
-        if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
-            const int ns = sc.n_spheres;
-            bool take = t < tr.t;
-            if (t == tr.t && tr.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (tr.prim - ns));
-            if (take) {
-                tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
-                if (any_hit) next = TRT_TRAV_DONE;
-            }
-        }
-    }
-    tr.node = next;
 }
 
 // One traversal step with a UNIFIED FETCH: whatever the lane is at — a 4-wide node (128 B) or a leaf's triangle
@@ -304,140 +239,30 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
         if (k0 < INF) { tr.node = r0; tr.sp = sp; }
         else { tr.node = stack[sp - 1]; tr.sp = sp - 1; }
     } else {
+        // a leaf is a RUN of triangles that share one box (bvh_build.cu, group_heads): 64-byte records idx, idx+1, ...;
+        // the head record carries the count.  The first record came with the unified fetch above.
         int next = stack[--tr.sp];
-        if (idx != src_leaf && idx != twin_leaf) {
-            float t, u, v;
-            if (COUNT) cnt.tri_tests++;
-            if (triangle_test(f0a, f0b, f1a, o, d, sc.tri_tmin, t, u, v)) {
-                const int ns = sc.n_spheres;
-                bool take = t < tr.t;
-                if (t == tr.t && tr.prim >= ns) take = __float_as_int(f1b.x) < __ldg(sc.tri_orig + (tr.prim - ns));
-                if (take) {
-                    tr.t = t; tr.prim = ns + idx; tr.u = u; tr.v = v;
-                    if (any_hit) next = TRT_TRAV_DONE;
-                }
-            }
-        }
-        tr.node = next;
-    }
-}
-
-// One traversal trip that serves BOTH of a lane's pending jobs: the 4-wide node in tr.node (if any) and the leaf parked in
-// `pend` (if any).  In the plain if-if loop a ray alternates between node trips and leaf trips, and the two code paths run
-// one after the other with the lanes split between them (ncu: 15.7 lanes at nodes, 6.2 at leaves).  Here a leaf that is
-// popped is parked and tested during the lane's next node visit, so a ray needs max(node visits, leaf tests) trips instead
-// of their sum, both record fetches are in flight together, and the leaf code runs for every lane that has a parked leaf.
-// The node visit of the same trip still uses the old tr.t (one visit of speculation at most; the result is unchanged).
-// CULL: stack entries carry the child's entry distance and are dropped at pop time once a closer hit is known.
-template <bool COUNT, bool CULL>
-__device__ __forceinline__ void bvh_step_dual(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
-                                              int src_leaf, int twin_leaf, bool any_hit, Trav& tr, int& pend,
-                                              int* stack, float* stack_t, TraceCounters& cnt)
-{
-    const float INF = __int_as_float(0x7f800000);
-    // ---- the parked leaf first: its hit shortens tr.t for the node visit below ----------------------------------
-    if (pend != 0) {
-        const int leaf_idx = ~pend;
-        pend = 0;
-        if (leaf_idx != src_leaf && leaf_idx != twin_leaf) {
-            const float4* rec = sc.tri + 4 * (size_t)leaf_idx;
-            float4 g0a, g0b, g1a, g1b;
-            ldg256(rec, g0a, g0b); ldg256(rec + 2, g1a, g1b);
-            float t, u, v;
-            if (COUNT) cnt.tri_tests++;
-            if (triangle_test(g0a, g0b, g1a, o, d, sc.tri_tmin, t, u, v)) {
-                const int ns = sc.n_spheres;
-                bool take = t < tr.t;
-                if (t == tr.t && tr.prim >= ns) take = __float_as_int(g1b.x) < __ldg(sc.tri_orig + (tr.prim - ns));
-                if (take) {
-                    tr.t = t; tr.prim = ns + leaf_idx; tr.u = u; tr.v = v;
-                    if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; }
-                }
-            }
-        }
-    }
-    if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) {
-        float4 f0a, f0b, f1a, f1b, f2a, f2b, f3a, f3b;
-        const float4* rec = sc.nodes + 8 * (size_t)tr.node;
-        const int rot = tr.node & 3;
-        ldg256(rec + 2 * ((0 + rot) & 3), f0a, f0b); ldg256(rec + 2 * ((1 + rot) & 3), f1a, f1b);
-        ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b); ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
-        if (COUNT) cnt.box_tests += 4;
-#define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
-    {                                                                                                      \
-        const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
-        const float ay = fmaf(LY, idir.y, -ood.y), by = fmaf(HY, idir.y, -ood.y);                          \
-        const float az = fmaf(LZ, idir.z, -ood.z), bz = fmaf(HZ, idir.z, -ood.z);                          \
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));           \
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
-        KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
-    }
-        float k0, k1, k2, k3;
-        int r0 = __float_as_int(f3a.x), r1 = __float_as_int(f3a.y), r2 = __float_as_int(f3a.z), r3 = __float_as_int(f3a.w);
-        TRT_SLAB(f0a.x, f0b.x, f1a.x, f1b.x, f2a.x, f2b.x, r0, k0)
-        TRT_SLAB(f0a.y, f0b.y, f1a.y, f1b.y, f2a.y, f2b.y, r1, k1)
-        TRT_SLAB(f0a.z, f0b.z, f1a.z, f1b.z, f2a.z, f2b.z, r2, k2)
-        TRT_SLAB(f0a.w, f0b.w, f1a.w, f1b.w, f2a.w, f2b.w, r3, k3)
-#undef TRT_SLAB
-        order2(k0, r0, k1, r1); order2(k2, r2, k3, r3);
-        order2(k0, r0, k2, r2); order2(k1, r1, k3, r3);
-        order2(k1, r1, k2, r2);
-        int sp = tr.sp;
-        if (k3 < INF) { stack[sp] = r3; if (CULL) stack_t[sp] = k3; sp++; }
-        if (k2 < INF) { stack[sp] = r2; if (CULL) stack_t[sp] = k2; sp++; }
-        if (k1 < INF) { stack[sp] = r1; if (CULL) stack_t[sp] = k1; sp++; }
-        tr.sp = sp;
-        tr.node = (k0 < INF) ? r0 : 0x7ffffffd;         // 0x7ffffffd: nothing in hand, pop below
-    }
-    // hand-over: a leaf in hand is parked (pend is free here), then the next entry is popped; with CULL, entries
-    // that start beyond the best hit are dropped on the way
-    if (tr.node < 0) { pend = tr.node; tr.node = 0x7ffffffd; }
-    if (tr.node == 0x7ffffffd) {
-        int sp = tr.sp, ref;
-        if (CULL) {
-            do { --sp; ref = stack[sp]; } while (ref != TRT_TRAV_DONE && stack_t[sp] > tr.t);
-        } else {
-            ref = stack[--sp];
-        }
-        tr.node = ref; tr.sp = sp;
-    }
-}
-
-// One traversal trip with DEFERRED leaves (speculative traversal, Aila & Laine 2009): a lane that reaches a
-// leaf parks it in `pend` and keeps descending; the triangle tests are executed for the whole warp only when
-// some lane cannot continue (it holds a parked leaf and found another, or ran out of nodes).  Leaf code then
-// runs with many lanes active instead of the 3-5 that happen to be at a leaf in any given trip.  The result is
-// unchanged: every leaf whose box the ray enters is still tested, and ties are broken by primitive index.
-// Must be called by all 32 lanes; `inside` = this lane still has work (node or parked leaf).
-template <bool COUNT>
-__device__ __forceinline__ void bvh_trip(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
-                                         int src_leaf, int twin_leaf, bool any_hit, bool inside,
-                                         Trav& tr, int& pend, int* stack, TraceCounters& cnt)
-{
-    if (inside) {
-        if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) bvh_visit<COUNT>(sc, idir, ood, tr, stack, cnt);
-        if (tr.node < 0 && pend == 0) { pend = tr.node; tr.node = stack[--tr.sp]; }
-    }
-    const bool stuck = inside && pend != 0 && (tr.node < 0 || tr.node == TRT_TRAV_DONE);
-    if (__any_sync(0xffffffffu, stuck)) {
-        if (inside && pend != 0) {
-            const int p = ~pend;
-            pend = 0;
+        int left = __float_as_int(f1b.w);
+        int p = idx;
+        for (;;) {
             if (p != src_leaf && p != twin_leaf) {
                 float t, u, v;
-                const float4 r0 = __ldg(sc.tri + 4 * p), r1 = __ldg(sc.tri + 4 * p + 1), r2 = __ldg(sc.tri + 4 * p + 2);
                 if (COUNT) cnt.tri_tests++;
-                if (triangle_test(r0, r1, r2, o, d, sc.tri_tmin, t, u, v)) {
+                if (triangle_test(f0a, f0b, f1a, o, d, sc.tri_tmin, t, u, v)) {
                     const int ns = sc.n_spheres;
                     bool take = t < tr.t;
-                    if (t == tr.t && tr.prim >= ns) take = __ldg(sc.tri_orig + p) < __ldg(sc.tri_orig + (tr.prim - ns));
+                    if (t == tr.t && tr.prim >= ns) take = __float_as_int(f1b.x) < __ldg(sc.tri_orig + (tr.prim - ns));
                     if (take) {
                         tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
-                        if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; }
+                        if (any_hit) { next = TRT_TRAV_DONE; left = 0; }
                     }
                 }
             }
+            if (--left <= 0) break;
+            p++; rec += 4;
+            ldg256(rec, f0a, f0b); ldg256(rec + 2, f1a, f1b);
         }
+        tr.node = next;
     }
 }
 

@@ -24,7 +24,7 @@ struct RenderArgs {
     uint32_t key0, key1;
     // work decomposition
     int chunk, n_chunks, tiles_x, tiles_y;
-    int min_steps, exit_num, vote;      // BVH-loop policy, see pathtrace.cu (vote = 1: deferred leaves, bvh_trip)
+    int min_steps, exit_num;            // BVH-loop policy, see pathtrace.cu
     int max_hk;                         // megakernel: housekeeping passes per trip
     int item_order;                     // see decode_item (trt_shade.cuh)
     int count_tests, wf_blocks, wf_check; // wavefront engine: count box/tri tests; trace CTAs per SM; waves between liveness checks
@@ -96,7 +96,7 @@ struct BuildOutputs {            // device buffers allocated by the caller with 
     int root;
     float tri_tmin;
     float3 root_lo, root_hi;   // padded bounds of all triangles
-    int max_depth, n_twins, n_wide_nodes, wide_depth, binary_depth;
+    int max_depth, n_twins, n_wide_nodes, wide_depth, binary_depth, n_groups;   // n_groups = leaves of the hierarchy (runs of equal boxes)
     double sah_cost;
 };
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream);

@@ -168,13 +168,12 @@ wf_trace_kernel(const __grid_constant__ RenderArgs A, const __grid_constant__ Wf
     bool any_hit = false;
     Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
     int stack[TRT_STACK_DEPTH];
-    int pend = 0;                           // parked leaf (0 = none), see bvh_trip
     unsigned ray_count = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
 
     for (;;) {
         // ---- finished queries out, next slots in -------------------------------------------------
-        if (slot >= 0 && tr.node == TRT_TRAV_DONE && pend == 0) {
+        if (slot >= 0 && tr.node == TRT_TRAV_DONE) {
             S.hit[slot] = make_float4(tr.t, __int_as_float(tr.prim), tr.u, tr.v);
             slot = -1;
         }
@@ -225,12 +224,11 @@ wf_trace_kernel(const __grid_constant__ RenderArgs A, const __grid_constant__ Wf
             const int src_leaf = src_prim - sc.n_spheres;
             const bool more = !(dry && pool_next >= pool_end);
             for (int step = 0;; step++) {
-                const bool inside = slot >= 0 && (tr.node != TRT_TRAV_DONE || pend != 0);
+                const bool inside = slot >= 0 && (tr.node != TRT_TRAV_DONE);
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
                 if (more && step >= A.min_steps && __popc(in_mask) < A.exit_num) break;
-                if (A.vote) bvh_trip<COUNT>(sc, o, d, idir, ood, src_leaf, src_twin, any_hit, inside, tr, pend, stack, cnt);
-                else if (inside) bvh_step_unified<COUNT>(sc, o, d, idir, ood, src_leaf, src_twin, any_hit, tr, stack, cnt);
+                if (inside) bvh_step_unified<COUNT>(sc, o, d, idir, ood, src_leaf, src_twin, any_hit, tr, stack, cnt);
             }
         }
     }
