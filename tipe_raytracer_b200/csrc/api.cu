@@ -160,6 +160,12 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.n_chunks = (spp + A.chunk - 1) / A.chunk;
     A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;
     A.n_items = (long long)A.tiles_x * A.tiles_y * A.n_chunks * 32;
+    {
+        auto magic = [](unsigned d) { unsigned long long m = (1ULL << 32) / d; return (unsigned)(m > 0xffffffffULL ? 0xffffffffULL : m); };
+        A.per_tile = 32u * (unsigned)A.n_chunks;
+        A.m_per_tile = magic(A.per_tile); A.m_chunks = magic((unsigned)A.n_chunks); A.m_tiles_x = magic((unsigned)A.tiles_x);
+        A.items_fit32 = (A.n_items + 64 < (1LL << 32)) ? 1 : 0;        // + the pool overshoot of the last reservations
+    }
     A.item_counter = d.ctrs;
     A.counters = d.ctrs + 1;
     A.accum = accum;

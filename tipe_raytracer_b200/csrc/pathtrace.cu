@@ -130,9 +130,8 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 if (need) {
                     if (item >= 0 && item < A.n_items) {
                         // item -> (tile, chunk, pixel in tile)
-                        int p, chunk, tile;
-                        decode_item(A, item, p, chunk, tile);
-                        const int tx = tile % A.tiles_x, ty = tile / A.tiles_x;
+                        int p, chunk, tile, tx, ty;
+                        decode_item(A, item, p, chunk, tile, tx, ty);
                         px = tx * 8 + (p & 7); py = ty * 4 + (p >> 3);
                         if (px < W && py < H) {
                             pixel = py * W + px;

@@ -30,13 +30,34 @@ struct PathResult {         // what one finished path adds to its pixel (col_alb
 // consecutive items cover one tile.  order 0: pixel fastest (32 consecutive items = the 32 pixels of the tile, one
 // chunk); order 1: chunk fastest (32 consecutive items = all chunks of 2-3 neighbouring pixels, so the lanes of a warp
 // start on nearly identical primary rays: coherent traversal, node fetches that coalesce).
-__device__ __forceinline__ void decode_item(const RenderArgs& A, long long item, int& p, int& chunk, int& tile)
+// x / d and x % d for x < 2^32 with a host-computed m = min(floor(2^32 / d), 2^32 - 1): the quotient estimate is at most
+// one short, one correction step makes it exact (an integer division costs 20 instructions, the 64-bit one 80).
+__device__ __forceinline__ unsigned fastdiv(unsigned x, unsigned d, unsigned m, unsigned& rem)
 {
+    unsigned q = __umulhi(x, m);
+    unsigned r = x - q * d;
+    if (r >= d) { q++; r -= d; }
+    rem = r;
+    return q;
+}
+
+__device__ __forceinline__ void decode_item(const RenderArgs& A, long long item, int& p, int& chunk, int& tile, int& tx, int& ty)
+{
+    if (A.items_fit32) {
+        unsigned local, t, c, x;
+        t = fastdiv((unsigned)item, A.per_tile, A.m_per_tile, local);
+        if (A.item_order == 0) { p = (int)(local & 31u); chunk = (int)(local >> 5); }
+        else { p = (int)fastdiv(local, (unsigned)A.n_chunks, A.m_chunks, c); chunk = (int)c; }
+        tile = (int)t;
+        ty = (int)fastdiv(t, (unsigned)A.tiles_x, A.m_tiles_x, x); tx = (int)x;
+        return;
+    }
     const int per_tile = 32 * A.n_chunks;
     tile = (int)(item / per_tile);
     const int local = (int)(item - (long long)tile * per_tile);
     if (A.item_order == 0) { p = local & 31; chunk = local >> 5; }
     else { chunk = local % A.n_chunks; p = local / A.n_chunks; }
+    tx = tile % A.tiles_x; ty = tile / A.tiles_x;
 }
 
 // fill_canva's per-sample set-up (main.c:265-271) + get_ray (camera.h:42-54): the primary ray of (pixel, sample).

@@ -101,9 +101,8 @@ wf_shade_kernel(const __grid_constant__ RenderArgs A, const __grid_constant__ Wf
             if (need) {
                 const long long item = (long long)base + __popc(need_mask & lanemask_lt());
                 if (item < A.n_items) {
-                    int p, chunk, tile;
-                    decode_item(A, item, p, chunk, tile);
-                    const int tx = tile % A.tiles_x, ty = tile / A.tiles_x;
+                    int p, chunk, tile, tx, ty;
+                    decode_item(A, item, p, chunk, tile, tx, ty);
                     const int px = tx * 8 + (p & 7), py = ty * 4 + (p >> 3);
                     if (px < A.W && py < A.H) {
                         pixel = py * A.W + px;
