@@ -27,7 +27,7 @@
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
-template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER>
 __global__ void __launch_bounds__(PT_THREADS, PT_MIN_BLOCKS)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
@@ -60,6 +60,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     const bool fuse_ao = !HAS_TRIS && A.use_ao;      // sphere-only scenes: AO ray + next bounce ray in one scan
     Trav tr; tr.node = TRT_TRAV_DONE; tr.sp = 0; tr.t = 0.0f; tr.prim = TRT_NO_PRIM; tr.u = tr.v = 0.0f;
     int stack[TRT_STACK_DEPTH];
+    int pend = 0;                           // DEFER: the parked leaf (0 = none), see bvh_trip_deferred
 
     unsigned ray_count = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
@@ -76,11 +77,11 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         bool new_ray = false;
         if (COUNT) {
             sc_hk++;
-            sc_consume += __popc(__ballot_sync(0xffffffffu, tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)));
+            sc_consume += __popc(__ballot_sync(0xffffffffu, tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)));
         }
 
         // ---- A1. lanes whose query is complete: consume the hit (one trip of main.c:132-239) -------
-        if (tr.node == TRT_TRAV_DONE && (phase == PH_BOUNCE || phase == PH_AO)) {
+        if (tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)) {
             PathResult res;
             if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res, fuse_ao)) {
                 my_acc[0 * PT_THREADS] += to_fixed(res.L.x);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z);
@@ -172,8 +173,8 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             }
         }
         if (!HAS_TRIS || BRUTE || hk + 1 >= A.max_hk) break;
-        const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE));
-        const int n_ready = __popc(__ballot_sync(0xffffffffu, phase != PH_DONE && tr.node == TRT_TRAV_DONE));
+        const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE || pend != 0));
+        const int n_ready = __popc(__ballot_sync(0xffffffffu, phase != PH_DONE && tr.node == TRT_TRAV_DONE && pend == 0));
         if (n_ready == 0 || n_inside >= ((A.exit_num * __popc(live_mask) + 31) >> 5)) break;
       }
       if (live_mask == 0) break;
@@ -187,7 +188,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
             const int src_leaf = P.src_prim - sc.n_spheres, twin_leaf = P.src_twin;
             const int exit_below = (A.exit_num * __popc(live_mask) + 31) >> 5;
             for (int step = 0;; step++) {
-                const bool inside = tr.node != TRT_TRAV_DONE;
+                const bool inside = tr.node != TRT_TRAV_DONE || pend != 0;
                 const unsigned in_mask = __ballot_sync(0xffffffffu, inside);
                 if (in_mask == 0) break;
                 if (step >= A.min_steps && __popc(in_mask) < exit_below) break;
@@ -199,7 +200,8 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
                 // if-if: every trip, each lane does whatever it is at — a node visit or a leaf test (measured faster than
                 // deferring, voting on or pairing the two on B200, profiles/README.md)
-                if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
+                if (DEFER) bvh_trip_deferred<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, A.defer, tr, pend, stack, cnt);
+                else if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
             }
         }
     }
@@ -281,10 +283,10 @@ cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, 
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
 {
-    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT><<<grid, PT_THREADS, smem, stream>>>(A);
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 
@@ -297,6 +299,8 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
+    if (A.defer > 0) return count_tests ? launch_variant<true, false, true, true>(A, grid, smem, stream)
+                                        : launch_variant<true, false, false, true>(A, grid, smem, stream);
     return count_tests ? launch_variant<true, false, true>(A, grid, smem, stream)
                        : launch_variant<true, false, false>(A, grid, smem, stream);
 }
