@@ -200,7 +200,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
                 // if-if: every trip, each lane does whatever it is at — a node visit or a leaf test (measured faster than
                 // deferring, voting on or pairing the two on B200, profiles/README.md)
-                if (DEFER) bvh_trip_deferred<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, pend, stack, cnt);
+                if (DEFER) bvh_trip_deferred<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, A.defer, tr, pend, stack, cnt);
                 else if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
             }
         }
