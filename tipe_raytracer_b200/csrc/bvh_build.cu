@@ -181,37 +181,13 @@ __global__ void group_first(int n, const int* __restrict__ head, const int* __re
     if (p < n && head[p]) gfirst[gpos[p]] = p;
 }
 
-// The head record of every leaf carries the number of triangles of the run, NEGATED when the run is PLANAR: all its
-// triangles lie in one plane (the halves of a quad and their back-facing copies).  Triangles of one plane that a ray
-// meets are met at the same distance, so after the first accepted test of a planar run no other member can be closer
-// (members are tested in the caller's order, so on an exact tie the lower index has already won): the loop stops there.
-__global__ void group_counts(int n_groups, int n, const int* __restrict__ gfirst, const unsigned long long* __restrict__ keys,
-                             const double* __restrict__ raw, int planar_on, float4* tri)
+// the head record of every leaf carries the number of triangles of the run
+__global__ void group_counts(int n_groups, int n, const int* __restrict__ gfirst, float4* tri)
 {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     const int first = gfirst[g], next = (g + 1 < n_groups) ? gfirst[g + 1] : n;
-    const int count = next - first;
-    bool planar = planar_on && count >= 2 && count <= 16;
-    if (planar) {
-        const double* a = raw + 25 * (size_t)(keys[first] & IDX_MASK);
-        const double ab[3] = {a[3] - a[0], a[4] - a[1], a[5] - a[2]}, ac[3] = {a[6] - a[0], a[7] - a[1], a[8] - a[2]};
-        const double n0[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
-        const double len2 = n0[0] * n0[0] + n0[1] * n0[1] + n0[2] * n0[2];
-        double scale2 = 0.0;                                                   // squared extent of the run
-        for (int m = 0; m < count && planar; m++) {
-            const double* b = raw + 25 * (size_t)(keys[first + m] & IDX_MASK);
-            for (int v = 0; v < 3; v++) {
-                const double e[3] = {b[3 * v] - a[0], b[3 * v + 1] - a[1], b[3 * v + 2] - a[2]};
-                const double dist = e[0] * n0[0] + e[1] * n0[1] + e[2] * n0[2];      // * |n0| = distance to the plane
-                const double e2 = e[0] * e[0] + e[1] * e[1] + e[2] * e[2];
-                if (e2 > scale2) scale2 = e2;
-                if (dist * dist > 1e-20 * len2 * (scale2 > 0.0 ? scale2 : 1.0)) planar = false;    // farther than 1e-10 of the run's size
-            }
-        }
-        if (!(len2 > 0.0)) planar = false;
-    }
-    tri[4 * first + 3].w = __int_as_float(planar ? -count : count);
+    tri[4 * first + 3].w = __int_as_float(next - first);
 }
 
 __device__ __forceinline__ bool same_point(const double* a, const double* b) { return a[0] == b[0] && a[1] == b[1] && a[2] == b[2]; }
@@ -555,10 +531,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     emit_leaves<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, in.quel_mat, box_lo, box_hi, pad,
                                           out.tri, out.tri_uv, out.tri_orig, leaf_lo, leaf_hi);
     find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, out.tri, small + 9);
-    {
-        const char* pl = getenv("TRT_TUNE_PLANAR");
-        group_counts<<<(n_groups + TB - 1) / TB, TB, 0, stream>>>(n_groups, n, gfirst, keys_b, in.tris_raw, (pl && *pl && atoi(pl) == 0) ? 0 : 1, out.tri);
-    }
+    group_counts<<<(n_groups + TB - 1) / TB, TB, 0, stream>>>(n_groups, n, gfirst, out.tri);
     BT(cudaGetLastError());
     out.n_groups = n_groups;
     if (n_groups == 1) {

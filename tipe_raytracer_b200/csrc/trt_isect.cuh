@@ -243,8 +243,6 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
         // the head record carries the count.  The first record came with the unified fetch above.
         int next = stack[--tr.sp];
         int left = __float_as_int(f1b.w);
-        const bool planar = left < 0;               // a run in one plane: the first accepted test settles it (bvh_build.cu, group_counts)
-        left = abs(left);
         int p = idx;
         for (;;) {
             if (p != src_leaf && p != twin_leaf) {
@@ -258,7 +256,6 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
                         tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
                         if (any_hit) { next = TRT_TRAV_DONE; left = 0; }
                     }
-                    if (planar) left = 0;
                 }
             }
             if (--left <= 0) break;
@@ -325,8 +322,6 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
             float4 f0a, f0b, f1a, f1b;
             ldg256(rec, f0a, f0b); ldg256(rec + 2, f1a, f1b);
             int left = __float_as_int(f1b.w);
-            const bool planar = left < 0;           // a run in one plane: the first accepted test settles it (bvh_build.cu, group_counts)
-            left = abs(left);
             for (;;) {
                 if (p != src_leaf && p != twin_leaf) {
                     float t, u, v;
@@ -339,7 +334,6 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
                             tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
                             if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; left = 0; }
                         }
-                        if (planar) left = 0;
                     }
                 }
                 if (--left <= 0) break;
