@@ -62,7 +62,8 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b)
     return f3(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
 }
 __device__ __forceinline__ float3 fma3(float3 a, float s, float3 b) { return f3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }
-__device__ __forceinline__ float3 normalize3(float3 a) { float r = rsqrtf(dot3(a, a)); return a * r; }
+__device__ __forceinline__ float rsq_approx(float x);
+__device__ __forceinline__ float3 normalize3(float3 a) { float r = rsq_approx(dot3(a, a)); return a * r; }
 __device__ __forceinline__ float3 lerp3(float3 a, float3 b, float t) { return fma3(b - a, t, a); }   // rtutility.h:32-34
 __device__ __forceinline__ float3 xyz(float4 v) { return f3(v.x, v.y, v.z); }
 
@@ -115,6 +116,14 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
+}
+
+// MUFU.RSQ without rsqrtf()'s denormal-input rescue (4 more instructions); callers pass values far from 1e-38
+__device__ __forceinline__ float rsq_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ float rcp_approx(float x)

@@ -34,7 +34,7 @@ __device__ __forceinline__ float sphere_root(float4 cr, float3 o, float3 d, floa
     if (on_surface) c = 0.0f;
     const float qd = fmaf(hb, hb, -a * c);                          // discriminant / 4
     if (!(qd > 0.0f)) return -1.0f;                                 // sphere.h:27 (strict)
-    const float sq = qd * rsqrtf(qd);                               // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL
+    const float sq = qd * rsq_approx(fmaxf(qd, 1e-36f));      // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL (qd > 0 here; the floor keeps a denormal qd from flushing to 1/0)                               // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL
     const float q = -(hb + copysignf(sq, hb));                      // never cancels
     const float ra = q * inv_a;
     const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* _
             const float hb = dot3(oc, d);
             const float qd = fmaf(hb, hb, -a * c);
             if (qd > 0.0f) {
-                const float sq = qd * rsqrtf(qd);
+                const float sq = qd * rsq_approx(fmaxf(qd, 1e-36f));      // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL (qd > 0 here; the floor keeps a denormal qd from flushing to 1/0)
                 const float q = -(hb + copysignf(sq, hb));
                 const float ra = q * inv_a;
                 const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
