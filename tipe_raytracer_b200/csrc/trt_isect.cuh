@@ -161,10 +161,12 @@ __device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* _
         const float3 oc = f3(o.x - cr.x, o.y - cr.y, o.z - cr.z);
         float c = fmaf(oc.x, oc.x, fmaf(oc.y, oc.y, fmaf(oc.z, oc.z, -cr.w * cr.w)));
         if (k == src_prim) c = 0.0f;
-        if (do_bounce) {
+        // both queries are evaluated for every lane and masked by do_bounce / do_ao (a lane usually has both; branching
+        // around each costs a reconvergence barrier per sphere); only the root computation stays behind a branch
+        {
             const float hb = dot3(oc, d);
             const float qd = fmaf(hb, hb, -a * c);
-            if (qd > 0.0f) {
+            if (qd > 0.0f && do_bounce) {
                 const float sq = qd * rsq_approx(fmaxf(qd, 1e-36f));      // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL (qd > 0 here; the floor keeps a denormal qd from flushing to 1/0)
                 const float q = -(hb + copysignf(sq, hb));
                 const float ra = q * inv_a;
@@ -174,11 +176,11 @@ __device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* _
                 if (t >= 0.0f && t < tr.t) { tr.t = t; tr.prim = k; }
             }
         }
-        if (do_ao) {
+        {
             const float hb = dot3(oc, d_ao);
             const float qd = fmaf(hb, hb, -a2 * c);
             const float e = eps2 + hb;
-            occluded = occluded || (qd > 0.0f && (e <= 0.0f || qd >= e * e));
+            occluded = occluded | (do_ao & (qd > 0.0f) & ((e <= 0.0f) | (qd >= e * e)));
         }
     }
     if (COUNT) cnt.sphere_tests += ns * ((do_bounce ? 1 : 0) + (do_ao ? 1 : 0));
