@@ -37,7 +37,7 @@ __device__ __forceinline__ float sphere_root(float4 cr, float3 o, float3 d, floa
     const float sq = qd * rsq_approx(fmaxf(qd, 1e-36f));      // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL (qd > 0 here; the floor keeps a denormal qd from flushing to 1/0)                               // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL
     const float q = -(hb + copysignf(sq, hb));                      // never cancels
     const float ra = q * inv_a;
-    const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
+    const float rb = (q != 0.0f) ? c * rcp_approx(q) : 0.0f;         // MUFU.RCP + FMUL (__fdividef adds a 5-instruction range rescue for |q| > 2^126)
     const float t1 = fminf(ra, rb), t2 = fmaxf(ra, rb);
     if (t1 >= 1e-4f) return t1;                                     // sphere.h:29
     if (t2 >= 1e-4f) return t2;                                     // sphere.h:38
@@ -170,7 +170,7 @@ __device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* _
                 const float sq = qd * rsq_approx(fmaxf(qd, 1e-36f));      // sqrt(qd), 2 ulp: MUFU.RSQ + FMUL (qd > 0 here; the floor keeps a denormal qd from flushing to 1/0)
                 const float q = -(hb + copysignf(sq, hb));
                 const float ra = q * inv_a;
-                const float rb = (q != 0.0f) ? __fdividef(c, q) : 0.0f;
+                const float rb = (q != 0.0f) ? c * rcp_approx(q) : 0.0f;         // MUFU.RCP + FMUL (__fdividef adds a 5-instruction range rescue for |q| > 2^126)
                 const float t1 = fminf(ra, rb), t2 = fmaxf(ra, rb);
                 const float t = (t1 >= 1e-4f) ? t1 : ((t2 >= 1e-4f) ? t2 : -1.0f);
                 if (t >= 0.0f && t < tr.t) { tr.t = t; tr.prim = k; }
