@@ -189,6 +189,12 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # stdout carries exactly ONE line, the JSON: whatever libraries print on fd 1 (NCCL's version banner, ...) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    json_out = os.fdopen(json_fd, "w")
+
     import torch
     import torch.distributed as dist
     import tipe_raytracer_b200 as trt
@@ -199,7 +205,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner must not share stdout with the JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -359,7 +364,8 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     r.close()
     if world > 1:
         dist.destroy_process_group()
