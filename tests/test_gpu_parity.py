@@ -223,6 +223,58 @@ def test_bvh_equals_linear_scan(rt):
     assert 0 < per_ray < 60, per_ray                 # vs 5 812 for the linear scan
 
 
+def _synthetic_scene(tris_abc, spp=4, bounces=3):
+    """A scene of hand-made triangles (one 2x2 white texture) under the emissive sky sphere, seen from +z."""
+    n = len(tris_abc)
+    tris = np.zeros(n, S.TRIANGLE)
+    for k, (a, b, c) in enumerate(tris_abc):
+        tris[k]["A"], tris[k]["B"], tris[k]["C"] = a, b, c
+        tris[k]["uvA"], tris[k]["uvB"], tris[k]["uvC"] = (0, 0), (1, 0), (0, 1)
+    mats = np.zeros(4, S.MATERIAL)
+    mats["diffuseColor"] = (0.8, 0.7, 0.6); mats["alpha"] = 1.0
+    return S.Scene(name="synthetic", spheres=S.spheres([S.sky_sphere()]), triangles=tris, mat_list=mats, tex_w=2, tex_h=2,
+                   nb_materials=1, quel_mat_pour_tri=np.zeros(n, np.int32), overrides=np.zeros(0, S.MAT_OVERRIDE),
+                   cam_origin=(0.3, 0.4, 4.0), cam_target=(0.0, 0.0, 0.0), vfov=40.0, ratio=4.0 / 3.0, width=96, spp=spp, bounces=bounces)
+
+
+@pytest.mark.parametrize("case", ["one_triangle", "one_box_40_triangles", "exact_duplicates", "two_boxes_interleaved"])
+def test_leaf_runs_edge_cases(rt, oracle, case):
+    """Leaves are runs of triangles with identical boxes (bvh_build.cu, group_heads): a single triangle (the root is a leaf), one
+    box shared by 40 triangles (the whole mesh is one run, longer than any run of the reference's meshes), exact duplicates (the
+    lower caller index must win the tie, main.c:85 strict '<'), and equal-centre boxes of different size (runs that interleave in
+    Morton order).  Checked three ways: primary ids against the FP64 oracle, BVH == linear scan bit for bit, image against the
+    oracle on the same Philox stream."""
+    rng = np.random.default_rng(3)
+    quad = [(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)]
+    if case == "one_triangle":
+        tris = [((-1, -1, 0), (1, -1, 0), (0, 1, 0))]
+    elif case == "one_box_40_triangles":
+        tris = []
+        for k in range(20):            # fans over the same square at slightly different depths: every box is [-1,1]^2 x [-0.2,0.2]
+            z = -0.2 + 0.4 * rng.random(4); z[rng.integers(0, 4)] = -0.2; z[(np.argmin(z) + 2) % 4] = 0.2
+            p = [(x, y, float(zz)) for (x, y, _), zz in zip(quad, z)]
+            tris += [(p[0], p[1], p[2]), (p[0], p[2], p[3])]
+        tris = [t for t in tris]
+    elif case == "exact_duplicates":
+        base = [(quad[0], quad[1], quad[2]), (quad[0], quad[2], quad[3])]
+        tris = base + base + [((-0.5, -0.5, 0.5), (0.5, -0.5, 0.5), (0.0, 0.5, 0.5))] * 3
+    else:
+        big = [(quad[0], quad[1], quad[2]), (quad[0], quad[2], quad[3])]
+        small = [tuple((0.5 * x, 0.5 * y, 0.25) for (x, y, _) in t) for t in big]
+        tris = [big[0], small[0], big[1], small[1]]
+    sc = _synthetic_scene(tris)
+    rt.scene_set(sc)
+    rp = S.params_for(sc)
+    prim_g, prim_o = rt.primary(rp), oracle.primary(sc, rp)
+    assert np.array_equal(prim_g["id"], prim_o["id"]) and (prim_g["id"] >= 1).mean() > 0.05
+    a = rt.render(rp)
+    b = rt.render(S.params_for(sc, flags=FLAG_BRUTE_FORCE))
+    assert np.array_equal(a["canva"], b["canva"]) and np.array_equal(a["albedo"], b["albedo"]) and a["stats"]["rays"] == b["stats"]["rays"]
+    o = oracle.render(sc, rp, rng=RNG_PHILOX)
+    assert (np.abs(a["canva"] - o["canva"]).max(axis=1) <= 1).mean() >= 0.97
+    assert abs(a["stats"]["rays"] / o["stats"]["rays"] - 1) < 5e-3
+
+
 # ---- 2b. radiance, statistical, against the reference's own rand() stream --------------------------------
 def test_render_c1_statistical_vs_reference(rt, oracle):
     sc = S.cornell_spheres()
