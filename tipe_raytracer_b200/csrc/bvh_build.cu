@@ -162,15 +162,20 @@ __global__ void emit_leaves(int n, const unsigned long long* __restrict__ keys, 
 
 // head[p] = 1 when the triangle at sorted position p starts a new box (group == 0: every triangle is its own leaf)
 __global__ void group_heads(int n, const unsigned long long* __restrict__ keys, const float4* __restrict__ box_lo,
-                            const float4* __restrict__ box_hi, int group, int* head)
+                            const float4* __restrict__ box_hi, int group, int cap, int* head)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int h = 1;
     if (p > 0 && group) {
-        const int k = (int)(keys[p] & IDX_MASK), q = (int)(keys[p - 1] & IDX_MASK);
-        const float4 a = box_lo[k], b = box_hi[k], c = box_lo[q], d = box_hi[q];
-        h = !(a.x == c.x && a.y == c.y && a.z == c.z && b.x == d.x && b.y == d.y && b.z == d.z);
+        // walk back to the start of the run of equal boxes (at most cap - 1 steps): a run is cut every `cap` triangles
+        int back = 0;
+        for (int q = p; q > 0 && back < cap; q--, back++) {
+            const int k = (int)(keys[q] & IDX_MASK), k2 = (int)(keys[q - 1] & IDX_MASK);
+            const float4 a = box_lo[k], b = box_hi[k], c = box_lo[k2], d = box_hi[k2];
+            if (!(a.x == c.x && a.y == c.y && a.z == c.z && b.x == d.x && b.y == d.y && b.z == d.z)) break;
+        }
+        h = (back == 0 || back >= cap) ? 1 : 0;      // back == 0: the box differs from the previous triangle's; back == cap: cut
     }
     head[p] = h;
 }
@@ -508,7 +513,9 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     BT(cudaGetLastError());
     BT(cub::DeviceRadixSort::SortKeys(base + o_cub, cub_bytes, keys_a, keys_b, n, 0, 64, stream));
 
-    group_heads<<<grid_n, TB, 0, stream>>>(n, keys_b, box_lo, box_hi, group, ghead);
+    const char* capv = getenv("TRT_TUNE_RUNCAP");
+    const int run_cap = (capv && *capv && atoi(capv) > 0) ? atoi(capv) : 16;
+    group_heads<<<grid_n, TB, 0, stream>>>(n, keys_b, box_lo, box_hi, group, run_cap, ghead);
     { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, ghead, gpos, n, stream)); }
     group_first<<<grid_n, TB, 0, stream>>>(n, ghead, gpos, gfirst);
     BT(cudaGetLastError());
