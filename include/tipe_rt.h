@@ -98,7 +98,9 @@ TRT_API int trt_default_overrides(trt_mat_override* out, int capacity);
 enum {
     TRT_FLAG_COUNT_RAYS  = 1 << 0,   /* fill trt_stats.rays (one 64-bit atomic per warp per item) */
     TRT_FLAG_BRUTE_FORCE = 1 << 1,   /* triangles by linear scan like main.c:81-90 instead of the BVH */
-    TRT_FLAG_COUNT_TESTS = 1 << 2    /* also count box / triangle / sphere tests (slower; for the roofline) */
+    TRT_FLAG_COUNT_TESTS = 1 << 2,   /* also count box / triangle / sphere tests (slower; for the roofline) */
+    TRT_FLAG_TILE_SPLIT  = 1 << 3    /* trt_render on several devices: split the image by interleaved 8x4 tiles (device k takes the
+                                        tiles k mod N with ALL samples) instead of by sample ranges; same image bit for bit */
 };
 typedef struct trt_params {
     int        largeur_image, hauteur_image;     /* W, H */
@@ -112,7 +114,8 @@ typedef struct trt_params {
     int        sample_offset;                    /* global index of this call's first sample (spp split) */
     int        sample_total;                     /* divisor used by the resolve; 0 => nbRayonParPixel */
     int        flags;
-    int        reserved;
+    int        tile_part;                        /* 0: the whole image.  Else part | n_parts << 16: this call renders only the 8x4
+                                                    tiles t with t mod n_parts == part (tile split across processes) */
 } trt_params;
 
 typedef struct trt_stats {

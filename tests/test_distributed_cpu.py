@@ -33,6 +33,15 @@ def test_sample_ranges_tile_the_job():
     assert [p.sample_offset for p in weak] == [0, 10, 20, 30] and all(p.sample_total == 40 and p.spp == 10 for p in weak)
 
 
+def test_tile_split_rank_params():
+    sc = S.cornell_spheres()
+    rp = S.params_for(sc, width=64, spp=10)
+    parts = [D.rank_params(rp, r, 4, split="tile") for r in range(4)]
+    assert [p.tile_part & 0xffff for p in parts] == [0, 1, 2, 3] and all((p.tile_part >> 16) == 4 for p in parts)
+    assert all(p.spp == 10 and p.sample_offset == 0 and p.sample_total == 10 for p in parts)      # every rank: all samples, divisor = spp
+    assert D.rank_params(rp, 0, 1, split="tile").tile_part == 0
+
+
 def test_resolve_host_matches_oracle_tonemap(oracle):
     rng = np.random.default_rng(5)
     sums = rng.uniform(0, 40, (3, 64))

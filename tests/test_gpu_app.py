@@ -1,6 +1,7 @@
 """GPU tests of the reference-facing entry points: the plain-C host program (apps/main_b200.c), the
 fill_canva(ThreadData) mirror, in-process multi-GPU, and the mini OBJ/MTL/PPM scene that exercises
 texture overrides (light / glass / water ordinals of texture.h:71-87) and alpha cut-outs."""
+import dataclasses
 import os
 import subprocess
 
@@ -134,3 +135,35 @@ def test_in_process_multi_gpu_is_bit_identical():
     for k in ("canva", "albedo", "normal"):
         assert a[k].tobytes() == b[k].tobytes()
     assert a["stats"]["rays"] == b["stats"]["rays"]
+    # tile split (SURVEY §8e partitioning B): every device renders all samples of the tiles k mod N
+    two = trt.Renderer([0, 1]); two.scene_set(sc)
+    c = two.render(S.params_for(sc, width=160, spp=21, flags=trt.FLAG_TILE_SPLIT)); two.close()
+    for k in ("canva", "albedo", "normal"):
+        assert a[k].tobytes() == c[k].tobytes()
+    assert a["stats"]["rays"] == c["stats"]["rays"]
+
+
+def test_tile_parts_assemble_the_image(rt):
+    """trt_params.tile_part: the interleaved-tile parts of an image, rendered by separate calls (separate processes / GPUs in the
+    multi-process path) into one sum buffer, are the image of a single call, bit for bit; ragged size, mesh and sphere scenes."""
+    import torch
+    from tipe_raytracer_b200 import distributed as D
+    for sc, width, spp in ((S.cornell_spheres(), 150, 9), (S.nature_mesh(), 97, 5)):
+        rt.scene_set(sc)
+        rp = S.params_for(sc, width=width, spp=spp)
+        want = rt.render(rp)
+        n = rp.width * rp.height
+        acc = torch.zeros(9 * n, dtype=torch.int64, device="cuda")
+        rays = 0
+        for part in range(3):
+            rays += rt.accumulate(D.rank_params(rp, part, 3, split="tile"), acc.data_ptr())["rays"]
+        got = rt.resolve(rp, acc.data_ptr())
+        for k in ("canva", "albedo", "normal"):
+            assert got[k].tobytes() == want[k].tobytes()
+        assert rays == want["stats"]["rays"]
+        one_part = torch.zeros(9 * n, dtype=torch.int64, device="cuda")
+        rt.accumulate(D.rank_params(rp, 1, 3, split="tile"), one_part.data_ptr())
+        touched = (one_part.view(9, n) != 0).any(0).float().mean().item()
+        assert 0.2 < touched < 0.5                                   # a third of the tiles (sky / black pixels stay zero anyway)
+    with pytest.raises(trt.TrtError):
+        rt.accumulate(dataclasses.replace(rp, tile_part=5 | (3 << 16)), acc.data_ptr())

@@ -22,7 +22,7 @@ from .scene import RenderParams, Scene
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libtipe_rt.so")
 
-FLAG_COUNT_RAYS, FLAG_BRUTE_FORCE, FLAG_COUNT_TESTS = 1, 2, 4
+FLAG_COUNT_RAYS, FLAG_BRUTE_FORCE, FLAG_COUNT_TESTS, FLAG_TILE_SPLIT = 1, 2, 4, 8
 ACCUM_CHANNELS, ACCUM_FRAC_BITS = 9, 28
 
 # every symbol include/tipe_rt.h declares
@@ -58,7 +58,7 @@ class TrtParams(C.Structure):
         ("cam", C.c_double * 12),
         ("seed", C.c_uint64),
         ("sample_offset", C.c_int), ("sample_total", C.c_int),
-        ("flags", C.c_int), ("reserved", C.c_int),
+        ("flags", C.c_int), ("tile_part", C.c_int),
     ]
 
 
@@ -91,6 +91,7 @@ def make_params(rp: RenderParams) -> TrtParams:
         p.cam[k] = float(cam[k])
     p.seed = rp.seed
     p.sample_offset, p.sample_total, p.flags = rp.sample_offset, rp.sample_total, rp.flags
+    p.tile_part = rp.tile_part
     return p
 
 

@@ -185,12 +185,16 @@ int check_params(trt_ctx* ctx, const trt_params* p)
     if (p->nbRayonParPixel < 1) return fail(ctx, TRT_ERR_INVALID, "nbRayonParPixel must be >= 1");
     if (p->nbRebondMax < 0) return fail(ctx, TRT_ERR_INVALID, "nbRebondMax must be >= 0");
     if (p->sample_offset < 0 || p->sample_total < 0) return fail(ctx, TRT_ERR_INVALID, "negative sample_offset / sample_total");
+    if (p->tile_part != 0) {
+        const int part = p->tile_part & 0xffff, parts = (p->tile_part >> 16) & 0xffff;
+        if (parts < 1 || part >= parts) return fail(ctx, TRT_ERR_INVALID, "tile_part = %d: part %d of %d", p->tile_part, part, parts);
+    }
     if (!ctx->has_scene) return fail(ctx, TRT_ERR_NO_SCENE, "trt_scene_set has not been called");
     return TRT_OK;
 }
 
 // Launches K2 for `spp` samples starting at global sample `offset` into `accum` on device d.
-int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int offset, long long* accum)
+int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int offset, long long* accum, int tile_offset = 0, int tile_stride = 1)
 {
     RenderArgs A{};
     A.scene = d.scene;
@@ -238,7 +242,10 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     }
     A.n_chunks = (spp + A.chunk - 1) / A.chunk;
     A.tiles_x = (A.W + 7) / 8; A.tiles_y = (A.H + 3) / 4;
-    A.n_items = (long long)A.tiles_x * A.tiles_y * A.n_chunks * 32;
+    A.tile_offset = tile_offset; A.tile_stride = tile_stride < 1 ? 1 : tile_stride;
+    const long long n_tiles = (long long)A.tiles_x * A.tiles_y;
+    const long long my_tiles = n_tiles > A.tile_offset ? (n_tiles - A.tile_offset + A.tile_stride - 1) / A.tile_stride : 0;
+    A.n_items = my_tiles * A.n_chunks * 32;
     {
         auto magic = [](unsigned d) { unsigned long long m = (1ULL << 32) / d; return (unsigned)(m > 0xffffffffULL ? 0xffffffffULL : m); };
         A.per_tile = 32u * (unsigned)A.n_chunks;
@@ -535,7 +542,8 @@ TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_ac
     const double t0 = now_ms();
     DeviceCtx& d = ctx->devs[0];
     CU(ctx, cudaSetDevice(d.dev));
-    rc = launch_trace(ctx, d, params, params->nbRayonParPixel, params->sample_offset, (long long*)d_accum);
+    rc = launch_trace(ctx, d, params, params->nbRayonParPixel, params->sample_offset, (long long*)d_accum,
+                      params->tile_part ? (params->tile_part & 0xffff) : 0, params->tile_part ? ((params->tile_part >> 16) & 0xffff) : 1);
     if (rc != TRT_OK) return rc;
     CU(ctx, cudaStreamSynchronize(d.stream));
     if (stats) {
@@ -627,12 +635,17 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
     std::vector<const long long*> srcs;
     for (int k = 0; k < n_dev; k++) {
         DeviceCtx& d = ctx->devs[k];
-        const int s0 = (int)((long long)spp * k / n_dev), s1 = (int)((long long)spp * (k + 1) / n_dev);
+        // spp split (default): device k renders samples [k*spp/N, (k+1)*spp/N) of every pixel; tile split
+        // (TRT_FLAG_TILE_SPLIT, or a tile_part of the caller's own): all samples of the tiles k mod N
+        const bool tile_split = n_dev > 1 && (params->flags & TRT_FLAG_TILE_SPLIT) != 0 && params->tile_part == 0;
+        int s0 = (int)((long long)spp * k / n_dev), s1 = (int)((long long)spp * (k + 1) / n_dev);
+        int t_off = params->tile_part ? (params->tile_part & 0xffff) : 0, t_stride = params->tile_part ? ((params->tile_part >> 16) & 0xffff) : 1;
+        if (tile_split) { s0 = 0; s1 = spp; t_off = k; t_stride = n_dev; }
         CU(ctx, cudaSetDevice(d.dev));
         if ((rc = ensure_accum(ctx, d, npix)) != TRT_OK) return rc;
         CU(ctx, cudaMemsetAsync(d.accum, 0, sizeof(long long) * 9 * npix, d.stream));
         if (s1 > s0) {
-            if ((rc = launch_trace(ctx, d, params, s1 - s0, params->sample_offset + s0, d.accum)) != TRT_OK) return rc;
+            if ((rc = launch_trace(ctx, d, params, s1 - s0, params->sample_offset + s0, d.accum, t_off, t_stride)) != TRT_OK) return rc;
             launches += d.last_launches;
         } else {
             CU(ctx, cudaEventRecord(d.ev_a, d.stream));

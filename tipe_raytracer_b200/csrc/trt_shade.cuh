@@ -48,6 +48,7 @@ __device__ __forceinline__ void decode_item(const RenderArgs& A, long long item,
         t = fastdiv((unsigned)item, A.per_tile, A.m_per_tile, local);
         if (A.item_order == 0) { p = (int)(local & 31u); chunk = (int)(local >> 5); }
         else { p = (int)fastdiv(local, (unsigned)A.n_chunks, A.m_chunks, c); chunk = (int)c; }
+        t = t * (unsigned)A.tile_stride + (unsigned)A.tile_offset;       // tile split: the k-th tile of this launch
         tile = (int)t;
         ty = (int)fastdiv(t, (unsigned)A.tiles_x, A.m_tiles_x, x); tx = (int)x;
         return;
@@ -57,6 +58,7 @@ __device__ __forceinline__ void decode_item(const RenderArgs& A, long long item,
     const int local = (int)(item - (long long)tile * per_tile);
     if (A.item_order == 0) { p = local & 31; chunk = local >> 5; }
     else { chunk = local % A.n_chunks; p = local / A.n_chunks; }
+    tile = tile * A.tile_stride + A.tile_offset;
     tx = tile % A.tiles_x; ty = tile / A.tiles_x;
 }
 

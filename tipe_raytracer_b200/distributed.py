@@ -32,9 +32,13 @@ def sample_range(rank: int, world: int, spp_total: int) -> Tuple[int, int]:
     return lo, hi - lo
 
 
-def rank_params(rp: RenderParams, rank: int, world: int, weak: bool = False) -> RenderParams:
+def rank_params(rp: RenderParams, rank: int, world: int, weak: bool = False, split: str = "spp") -> RenderParams:
     """RenderParams for one rank.  weak=False: rp.spp is the job total, split over ranks (BASELINE C5).
-    weak=True: every rank renders rp.spp samples, the job has world*rp.spp (bench.py's scaling runs)."""
+    weak=True: every rank renders rp.spp samples, the job has world*rp.spp (bench.py's scaling runs).
+    split="tile" (SURVEY §8e partitioning B): every rank renders ALL samples of the interleaved 8x4 tiles t with
+    t mod world == rank; the other pixels of its sum buffer stay zero, so the same int64 reduce assembles the image."""
+    if split == "tile":
+        return dataclasses.replace(rp, tile_part=(rank | (world << 16)) if world > 1 else 0, sample_total=rp.sample_total or rp.spp)
     if weak:
         return dataclasses.replace(rp, sample_offset=rp.sample_offset + rank * rp.spp, sample_total=world * rp.spp)
     lo, n = sample_range(rank, world, rp.spp)

@@ -162,6 +162,7 @@ class RenderParams:
     sample_offset: int = 0
     sample_total: int = 0
     flags: int = 0
+    tile_part: int = 0                 # 0 = whole image, else part | n_parts << 16 (interleaved 8x4 tiles, trt_params.tile_part)
     main_c_truncation: bool = True
 
     def effective(self):
