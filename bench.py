@@ -322,7 +322,8 @@ def main():
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         fp32_peak = n_sm * 128 * 2 * sm_clock / 1e12                 # TFLOP/s
         achieved = rays_per_launch * f_ray / (kernel_ms * 1e-3) / 1e12
-        hbm_alg = 9 * 8 * npix * ((spp + 15) // 16)                 # int64 RED traffic of the flushes (one per 16-sample item), per launch
+        chunk = max(4, min(16, (spp + 10) // 20)) if sc.triangles.shape[0] > 0 else 16      # samples per item (api.cu)
+        hbm_alg = 9 * 8 * npix * ((spp + chunk - 1) // chunk)       # int64 RED traffic of the item flushes, per launch
         traffic = None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, from the committed ncu capture
             with open(os.path.join(ROOT, "profiles", "r01_traffic_c2.json")) as f:
