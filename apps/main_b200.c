@@ -8,6 +8,7 @@
  *   main_b200 [--scene readme|sky|none] [--obj F --mtl F] [--width W] [--ratio R] [--spp N] [--bounces N]
  *             [--ao 0|1] [--ao-intensity X] [--vfov D] [--origin x,y,z] [--target x,y,z] [--focus F]
  *             [--aperture ax,ay] [--seed S] [--gpus N] [--no-main-c-truncation] [--out file.ppm]
+ *             [--tile-split]        several GPUs: interleaved 8x4 tiles per GPU instead of sample ranges (same image)
  *             [--sky-image F.ppm]   lat-long sky on the LAST sphere (the lookup main.c:64-71 keeps commented out; sky_file, main.c:322)
  *
  * Build: gcc -O2 apps/main_b200.c -o apps/main_b200 -Ltipe_raytracer_b200 -ltipe_rt -lm -Wl,-rpath,'$ORIGIN/../tipe_raytracer_b200'
@@ -40,7 +41,7 @@ int main(int argc, char** argv)
     int nbRayonParPixel = 100, nbRebondMax = 5;
     int useAO = 1; double AO_intensity = 2.5;
     const char *obj_file = NULL, *mtl_file = NULL, *scene = "readme", *out_file = "out_b200.ppm", *sky_file = NULL;
-    unsigned long long seed = 1010; int n_gpus = 1, truncate_like_main_c = 1;
+    unsigned long long seed = 1010; int n_gpus = 1, truncate_like_main_c = 1, tile_split = 0;
 
     for (int k = 1; k < argc; k++) {
         const char* a = argv[k]; const char* v = k + 1 < argc ? argv[k + 1] : NULL;
@@ -55,6 +56,7 @@ int main(int argc, char** argv)
         else if (OPT("--seed")) seed = strtoull(v, NULL, 10); else if (OPT("--gpus")) n_gpus = atoi(v); else if (OPT("--out")) out_file = v;
         else if (OPT("--sky-image")) sky_file = v;
         else if (strcmp(a, "--no-main-c-truncation") == 0) truncate_like_main_c = 0;
+        else if (strcmp(a, "--tile-split") == 0) tile_split = 1;
         else { usage: fprintf(stderr, "usage: see the header of apps/main_b200.c (bad option `%s`)\n", a); return 2; }
     }
     int hauteur_image = (int)(largeur_image / ratio);
@@ -123,6 +125,7 @@ int main(int argc, char** argv)
     p.ouverture_x = truncate_like_main_c ? (double)(int)ouverture[0] : ouverture[0];
     p.ouverture_y = truncate_like_main_c ? (double)(int)ouverture[1] : ouverture[1];
     p.cam = cam; p.seed = seed;
+    if (tile_split) p.flags |= TRT_FLAG_TILE_SPLIT;
     trt_stats st;
     double t_render = now_s();
     if (trt_render(ctx, &p, canva, albedo_tab, normal_tab, &st) != TRT_OK) { fprintf(stderr, "trt_render: %s\n", trt_last_error(ctx)); return 1; }
