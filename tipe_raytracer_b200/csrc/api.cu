@@ -225,7 +225,8 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     const int chunk_max = engine == 2 ? knob("TRT_TUNE_WF_CHUNK", 16) : knob("TRT_TUNE_CHUNK", 16);
     A.min_steps = knob("TRT_TUNE_MIN_STEPS", engine == 2 ? 4 : 2);
     A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 10);
-    A.max_hk = knob("TRT_TUNE_MAX_HK", 4);
+    A.max_hk = knob("TRT_TUNE_MAX_HK", 3);
+    A.hk_min = knob("TRT_TUNE_HK_MIN", 28);          // another housekeeping pass while fewer than 28/32 of the live lanes have BVH work (and some lane has a hit to consume)
     A.defer = knob("TRT_TUNE_DEFER", 3);
     A.item_order = knob("TRT_TUNE_ORDER", d.scene.n_tris > 0 ? 1 : 0);   // meshes: a warp starts on the samples of 2-3 neighbouring pixels (coherent primary rays, +2-3 %); spheres: one tile (+5 %)
     A.count_tests = count_tests ? 1 : 0;

@@ -178,7 +178,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         if (!HAS_TRIS || BRUTE || hk + 1 >= A.max_hk) break;
         const int n_inside = __popc(__ballot_sync(0xffffffffu, tr.node != TRT_TRAV_DONE || pend != 0));
         const int n_ready = __popc(__ballot_sync(0xffffffffu, phase != PH_DONE && tr.node == TRT_TRAV_DONE && pend == 0));
-        if (n_ready == 0 || n_inside >= ((A.exit_num * __popc(live_mask) + 31) >> 5)) break;
+        if (n_ready == 0 || n_inside >= ((A.hk_min * __popc(live_mask) + 31) >> 5)) break;
       }
       if (live_mask == 0) break;
       const bool ao = (phase == PH_AO);
