@@ -155,10 +155,21 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
 
         // ---- A3. start a path: fill_canva's per-sample set-up (main.c:265-271) --------------------
         if (phase == PH_NEW && pixel >= 0 && s_cur < s_end && A.bounces <= 0) s_cur = s_end;   // main.c:132 never iterates: all sums stay 0
-        if (phase == PH_NEW && pixel >= 0 && s_cur < s_end) {
-            start_path(A, pixel, px, py, s_cur, P);
-            phase = PH_BOUNCE;
-            new_ray = true;
+        {
+            // lanes that need a new path wait until start_min of them do, or no lane of the warp has a path left (api.cu: 32 on
+            // sphere scenes = the warp's paths run in step, 1 on meshes = every lane re-arms on its own)
+            const bool want_start = phase == PH_NEW && pixel >= 0 && s_cur < s_end;
+            bool go = want_start;
+            if (A.start_min > 1) {
+                const unsigned ws = __ballot_sync(0xffffffffu, want_start);
+                const unsigned busy = __ballot_sync(0xffffffffu, phase == PH_BOUNCE || phase == PH_AO);
+                go = want_start && (__popc(ws) >= A.start_min || busy == 0);
+            }
+            if (go) {
+                start_path(A, pixel, px, py, s_cur, P);
+                phase = PH_BOUNCE;
+                new_ray = true;
+            }
         }
 
         // ---- A4. new rays: sphere scan, scene-box cull, traversal set-up ---------------------------

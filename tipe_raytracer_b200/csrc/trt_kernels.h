@@ -27,6 +27,7 @@ struct RenderArgs {
     int tile_offset, tile_stride;       // this launch owns the tiles tile_offset + k * tile_stride (tile split; 0 / 1 = all)
     unsigned per_tile, m_per_tile, m_chunks, m_tiles_x; int items_fit32;   // decode_item: divisors' reciprocals (fastdiv)
     int min_steps, exit_num;            // BVH-loop policy, see pathtrace.cu
+    int start_min;                      // megakernel: new paths start once this many lanes of the warp need one (or none has a path left)
     int max_hk, hk_min;                 // megakernel: housekeeping passes per trip; repeated while fewer than hk_min/32 of the live lanes have BVH work
     int defer;                          // megakernel: > 0 = deferred leaves, tested once 1/defer of the lanes inside hold one (bvh_trip_deferred)
     int item_order;                     // see decode_item (trt_shade.cuh)
