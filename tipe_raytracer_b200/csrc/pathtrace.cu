@@ -5,17 +5,20 @@
 //
 // Execution model (sm_100a, 148 SMs):
 //   * persistent CTAs, a multiple of the SM count; no per-pixel thread mapping;
-//   * the unit of scheduling is an ITEM = (pixel, chunk of <= S consecutive samples).  Items are
-//     numbered so that 32 consecutive items are the 8x4 pixel tile of one chunk; a warp reserves
-//     32 items at a time from one global counter (one atomic per 32 items) and hands them to its
-//     lanes as they run dry, so lanes never wait for each other's paths ("ray regeneration"):
-//     every trip of the main loop traces exactly one ray per live lane — a bounce ray or an
-//     ambient-occlusion ray — whatever bounce or sample the lane is at;
+//   * the unit of scheduling is an ITEM = (pixel, chunk of consecutive samples).  A warp reserves a block of consecutive
+//     items from one global counter (one atomic per block) and hands them to its lanes as they run dry.  Items are numbered
+//     pixel-fastest on sphere scenes (a block = one 8x4 tile at one chunk) and chunk-fastest on meshes (a block = the chunks
+//     of two or three neighbouring pixels: near-identical primary rays);
+//   * meshes: every lane re-arms on its own ("ray regeneration"), so a lane never waits for another lane's path; the BVH
+//     loop is resumable and is left as soon as too few lanes are still inside, leaves are deferred and tested for the warp
+//     together (trt_isect.cuh, bvh_trip_deferred);  sphere scenes: the lanes of a warp start their paths together and run
+//     them in step (RenderArgs.start_min), every trip is one sphere scan for all lanes;
 //   * a lane keeps the 9 sums of its item as int64 fixed point in shared memory (18 registers saved) and flushes them
 //     with 9 RED.ADD.64 when the item ends: integer adds commute, so the image is bit-identical for any
-//     schedule, any grid and any split of the samples over GPUs;
+//     schedule, any grid and any split of the samples or tiles over GPUs;
 //   * spheres (and their materials) are staged once per CTA into shared memory; BVH nodes,
-//     triangles and texels are read through the read-only path and live in L1/L2.
+//     triangles and texels are read through the read-only path and live in L1/L2 (the shared-memory carve-out is kept
+//     to what the resident CTAs need, so that L1 has 192 KB on meshes).
 #include "trt_shade.cuh"
 
 #define PT_THREADS 256
