@@ -28,8 +28,6 @@
 #ifndef PT_MIN_BLOCKS_MESH
 #define PT_MIN_BLOCKS_MESH 3      // mesh kernel: 80 registers, no spills, 24 warps/SM (C2 +0.6 %, C4 +1.6 % over 4 CTAs at 64 registers with 158 B of spills)
 #endif
-#define PT_POOL_SPHERES 32        // items a warp reserves per atomic: one per lane on sphere scenes,
-#define PT_POOL_MESH 64           // two per lane on meshes (the warp stays on neighbouring pixels longer: C2 +1.8 %, C4 +4.8 %; 128: C2 +0.7 %, C4 +7.5 %)
 // Traversal-loop exit policy (RenderArgs.min_steps / exit_num): a warp always takes min_steps BVH steps,
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
@@ -120,7 +118,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 const long long avail = pool_end - pool_next;
                 long long fresh = 0;
                 if (avail < want && !global_dry) {
-                    if (lane == 0) fresh = (long long)atomicAdd(A.item_counter, (unsigned long long)(HAS_TRIS ? PT_POOL_MESH : PT_POOL_SPHERES));
+                    if (lane == 0) fresh = (long long)atomicAdd(A.item_counter, (unsigned long long)A.pool);
                     fresh = __shfl_sync(0xffffffffu, fresh, 0);
                 }
                 long long item = -1;
@@ -130,7 +128,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
                 if (avail < want && !global_dry) {
                     pool_next = fresh + (want - avail);
-                    pool_end = fresh + (HAS_TRIS ? PT_POOL_MESH : PT_POOL_SPHERES);
+                    pool_end = fresh + A.pool;
                     if (fresh >= A.n_items) global_dry = true;
                 } else {
                     pool_next += min((long long)want, avail);

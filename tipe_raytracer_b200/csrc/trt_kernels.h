@@ -24,6 +24,7 @@ struct RenderArgs {
     uint32_t key0, key1;
     // work decomposition
     int chunk, n_chunks, tiles_x, tiles_y;
+    int pool;                           // items a warp reserves per atomic (megakernel)
     int tile_offset, tile_stride;       // this launch owns the tiles tile_offset + k * tile_stride (tile split; 0 / 1 = all)
     unsigned per_tile, m_per_tile, m_chunks, m_tiles_x; int items_fit32;   // decode_item: divisors' reciprocals (fastdiv)
     int min_steps, exit_num;            // BVH-loop policy, see pathtrace.cu
