@@ -185,6 +185,15 @@ int check_params(trt_ctx* ctx, const trt_params* p)
     if (p->nbRayonParPixel < 1) return fail(ctx, TRT_ERR_INVALID, "nbRayonParPixel must be >= 1");
     if (p->nbRebondMax < 0) return fail(ctx, TRT_ERR_INVALID, "nbRebondMax must be >= 0");
     if (p->sample_offset < 0 || p->sample_total < 0) return fail(ctx, TRT_ERR_INVALID, "negative sample_offset / sample_total");
+    // the ambient-occlusion term is 1/AO_intensity (main.c:115): 0 (what ThreadData's int truncation makes of 0.x, main.c:42)
+    // is a division by zero there and would saturate every sample here
+    if (p->useAO && !(p->AO_intensity > 0.0)) return fail(ctx, TRT_ERR_INVALID, "useAO needs AO_intensity > 0 (got %g)", p->AO_intensity);
+    // int64 sums: a sample is clamped to 2^20 at 2^28 fixed point = 2^48, so 2^14 saturated samples still fit with a sign bit to spare
+    {
+        const long long total = p->sample_total > 0 ? p->sample_total : p->nbRayonParPixel;
+        if (total > (1LL << 30) || (long long)p->sample_offset + p->nbRayonParPixel > (1LL << 30))
+            return fail(ctx, TRT_ERR_INVALID, "more than 2^30 samples per pixel");
+    }
     if (p->tile_part != 0) {
         const int part = p->tile_part & 0xffff, parts = (p->tile_part >> 16) & 0xffff;
         if (parts < 1 || part >= parts) return fail(ctx, TRT_ERR_INVALID, "tile_part = %d: part %d of %d", p->tile_part, part, parts);
@@ -204,6 +213,10 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.bounces = p->nbRebondMax;
     A.use_ao = p->useAO ? 1 : 0;
     A.inv_ao = (float)(1.0 / p->AO_intensity);
+    {
+        const long long total = p->sample_total > 0 ? p->sample_total : p->nbRayonParPixel;      // the same on every GPU / rank of a job
+        A.sample_clamp = total <= (1LL << 14) ? TRT_SAMPLE_CLAMP : (float)((double)(1LL << 34) / (double)total);
+    }
     A.emit_scale_ao = (float)(1.5 * p->AO_intensity);
     A.focus = (float)p->focus_distance;
     A.aperture_x = (float)p->ouverture_x; A.aperture_y = (float)p->ouverture_y;
@@ -232,6 +245,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.max_hk = knob("TRT_TUNE_MAX_HK", 3);
     A.hk_min = knob("TRT_TUNE_HK_MIN", 28);          // another housekeeping pass while fewer than 28/32 of the live lanes have BVH work (and some lane has a hit to consume)
     A.defer = knob("TRT_TUNE_DEFER", 3);
+    A.exp_flags = knob("TRT_TUNE_EXP", 0);
     A.item_order = knob("TRT_TUNE_ORDER", d.scene.n_tris > 0 ? 1 : 0);   // meshes: a warp starts on the samples of 2-3 neighbouring pixels (coherent primary rays, +2-3 %); spheres: one tile (+5 %)
     A.count_tests = count_tests ? 1 : 0;
     A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
@@ -267,7 +281,33 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.counters = d.ctrs + 1;
     A.accum = accum;
     CU(ctx, cudaMemsetAsync(d.ctrs, 0, sizeof(unsigned long long) * 16, d.stream));
-    if (engine == 2) {
+    // engine 3 = slot-pool kernel (pathtrace_pool.cu), opt-in (TRT_ENGINE=3): same image; measured slower than engine 1 so far
+    // (C2 38.3 vs 31.2 ms: 30 of 32 lanes inside the BVH loop instead of 23, but more L1 wavefronts and 20 warps per SM)
+    bool pool_engine = false;
+    if (knob("TRT_ENGINE", 0) == 3 && d.scene.n_tris > 0 && !brute && p->nbRebondMax >= 1 && p->nbRebondMax <= 8191 && spp < (1 << 26)) {
+        A.pp_slots = knob("TRT_TUNE_SLOTS_PER_WARP", 64);
+        if (A.pp_slots < 32) A.pp_slots = 32;
+        if (A.pp_slots > 64) A.pp_slots = 64;
+        A.pp_shade_at = knob("TRT_TUNE_SHADE_AT", A.pp_slots >= 64 ? 32 : A.pp_slots - 24);
+        if (A.pp_shade_at < 1) A.pp_shade_at = 1;
+        if (A.pp_shade_at > 32) A.pp_shade_at = 32;
+        A.pp_refill_min = knob("TRT_TUNE_REFILL_MIN", 8);
+        A.pp_exit_below = knob("TRT_TUNE_EXIT", 10);
+        if (A.pp_exit_below < 1) A.pp_exit_below = 1;
+        auto magic = [](unsigned d) { unsigned long long m = (1ULL << 32) / d; return (unsigned)(m > 0xffffffffULL ? 0xffffffffULL : m); };
+        A.pp_per_tile = 32u * (unsigned)spp;
+        A.pp_m_per_tile = magic(A.pp_per_tile); A.pp_m_spp = magic((unsigned)spp);
+        A.n_items = my_tiles * 32 * (long long)spp;                       // paths, edge-tile padding included
+        A.pool = knob("TRT_TUNE_POOL", spp < 256 ? 256 : (spp > 2048 ? 2048 : spp));
+        A.pp_fit32 = (A.n_items + 2 * (long long)A.pool < (1LL << 32)) ? 1 : 0;
+        pool_engine = trt_pool_smem_bytes(A) <= (size_t)200 * 1024 / 4;   // 4+ CTAs of 128 threads per SM must fit
+    }
+    if (pool_engine) {
+        CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+        CU(ctx, trt_launch_pathtrace_pool(A, d.n_sms, blocks_per_sm, count_tests, d.stream));
+        CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+        d.last_launches = 1;
+    } else if (engine == 2) {
         const long long real_items = (long long)A.W * A.H * A.n_chunks;
         long long want = knob("TRT_TUNE_SLOTS", 1 << 20);
         if (want > real_items) want = real_items;
@@ -290,7 +330,7 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
         CU(ctx, cudaEventRecord(d.ev_b, d.stream));
         d.last_launches = 1;
     }
-    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 12, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaMemcpyAsync(d.h_ctrs, d.ctrs, sizeof(unsigned long long) * 15, cudaMemcpyDeviceToHost, d.stream));
     return TRT_OK;
 }
 
@@ -308,6 +348,14 @@ void collect_stats(trt_ctx* ctx, const trt_params* p, trt_stats* st, bool traced
         }
         st->paths = (uint64_t)p->largeur_image * (uint64_t)p->hauteur_image * (uint64_t)p->nbRayonParPixel;
     }
+}
+
+// pathtrace_pool.cu raises counters[13] when a warp has been scheduling for 20 s without finishing (a bug, not a long frame)
+int check_watchdog(trt_ctx* ctx)
+{
+    for (auto& d : ctx->devs)
+        if (d.h_ctrs[14] != 0) return fail(ctx, TRT_ERR_CUDA, "path-tracing kernel gave up after 20 s on device %d (scheduler watchdog)", d.dev);
+    return TRT_OK;
 }
 
 double now_ms()
@@ -557,6 +605,7 @@ TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_ac
                       params->tile_part ? (params->tile_part & 0xffff) : 0, params->tile_part ? ((params->tile_part >> 16) & 0xffff) : 1);
     if (rc != TRT_OK) return rc;
     CU(ctx, cudaStreamSynchronize(d.stream));
+    if ((rc = check_watchdog(ctx)) != TRT_OK) return rc;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         collect_stats(ctx, params, stats, true);
@@ -679,6 +728,7 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
     CU(ctx, cudaEventRecord(root.ev_d, root.stream));
     if ((rc = copy_out(ctx, root, npix, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;
     for (auto& d : ctx->devs) { CU(ctx, cudaSetDevice(d.dev)); CU(ctx, cudaStreamSynchronize(d.stream)); }
+    if ((rc = check_watchdog(ctx)) != TRT_OK) return rc;
     if (stats) {
         memset(stats, 0, sizeof *stats);
         collect_stats(ctx, params, stats, true);
@@ -697,6 +747,7 @@ TRT_API int trt_primary(trt_ctx* ctx, const trt_params* params, double* t, int* 
 {
     int rc = check_params(ctx, params);
     if (rc != TRT_OK) return rc;
+    if (params->hauteur_image > 65535) return fail(ctx, TRT_ERR_INVALID, "trt_primary: at most 65535 rows (one grid row per image row)");
     DeviceCtx& d = ctx->devs[0];
     const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
     CU(ctx, cudaSetDevice(d.dev));

@@ -89,9 +89,9 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         if (tr.node == TRT_TRAV_DONE && pend == 0 && (phase == PH_BOUNCE || phase == PH_AO)) {
             PathResult res;
             if (consume_hit(A, s_sph, s_mat, pixel, s_cur, tr.t, tr.prim, tr.u, tr.v, P, phase, res, fuse_ao)) {
-                my_acc[0 * PT_THREADS] += to_fixed(res.L.x);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z);
-                my_acc[3 * PT_THREADS] += to_fixed(res.albedo.x); my_acc[4 * PT_THREADS] += to_fixed(res.albedo.y); my_acc[5 * PT_THREADS] += to_fixed(res.albedo.z);
-                my_acc[6 * PT_THREADS] += to_fixed(res.normal.x); my_acc[7 * PT_THREADS] += to_fixed(res.normal.y); my_acc[8 * PT_THREADS] += to_fixed(res.normal.z);
+                my_acc[0 * PT_THREADS] += to_fixed(res.L.x, A.sample_clamp);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y, A.sample_clamp);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z, A.sample_clamp);
+                my_acc[3 * PT_THREADS] += to_fixed(res.albedo.x, A.sample_clamp); my_acc[4 * PT_THREADS] += to_fixed(res.albedo.y, A.sample_clamp); my_acc[5 * PT_THREADS] += to_fixed(res.albedo.z, A.sample_clamp);
+                my_acc[6 * PT_THREADS] += to_fixed(res.normal.x, A.sample_clamp); my_acc[7 * PT_THREADS] += to_fixed(res.normal.y, A.sample_clamp); my_acc[8 * PT_THREADS] += to_fixed(res.normal.z, A.sample_clamp);
                 s_cur++;
                 phase = PH_NEW;
             } else {
@@ -311,6 +311,11 @@ static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cu
         if (v && *v) pct = atoi(v);
         if (pct > 100) pct = 100;
         cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        // more than ~460 spheres: the sphere table + the per-lane sums pass the 48 KB a kernel gets without asking
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
     }
     pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();

@@ -122,7 +122,9 @@ primary_kernel(const __grid_constant__ PrimaryArgs P)
             tu = fmod(tu, 1.0); tv = fmod(tv, 1.0);
             if (tu < 0) tu = ADD(tu, 1.0);
             if (tv < 0) tv = ADD(tv, 1.0);
-            const int x = (int)MUL(tu, (double)sc.tex_w), y = (int)MUL(tv, (double)sc.tex_h);
+            // a tiny negative uv + 1.0 rounds to exactly 1.0: x == tex_w reads past the slab (the reference has the same
+            // hazard on the host, texture.h:61-62); clamped like the FP32 path (trt_isect.cuh, triangle_material)
+            const int x = min((int)MUL(tu, (double)sc.tex_w), sc.tex_w - 1), y = min((int)MUL(tv, (double)sc.tex_h), sc.tex_h - 1);
             const int ordinal = sc.quel_mat[k];
             const size_t texel = (size_t)(y * sc.tex_w + x) + (size_t)sc.tex_h * (size_t)sc.tex_w * (size_t)ordinal;
             const float4 m0 = sc.texels[3 * texel];

@@ -102,9 +102,11 @@ __device__ __forceinline__ float3 unit_sphere(float u, float v)
 
 // ---- fixed-point accumulation --------------------------------------------------------------------
 // Integer sums are associative: the image does not depend on which lane / GPU added which sample.
-__device__ __forceinline__ long long to_fixed(float v)
+// clamp = RenderArgs.sample_clamp: 2^20 for up to 2^14 samples per pixel, 2^34 / samples beyond, so that even a pixel whose
+// every sample saturates cannot wrap the int64 sum (2^28 * 2^34 = 2^62)
+__device__ __forceinline__ long long to_fixed(float v, float clamp)
 {
-    v = (v != v) ? 0.0f : fminf(fmaxf(v, -TRT_SAMPLE_CLAMP), TRT_SAMPLE_CLAMP);
+    v = (v != v) ? 0.0f : fminf(fmaxf(v, -clamp), clamp);
     return __float2ll_rn(v * TRT_ACCUM_SCALE);
 }
 
@@ -117,6 +119,8 @@ __device__ __forceinline__ void ldg256(const float4* p, float4& a, float4& b)
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // MUFU.RSQ without rsqrtf()'s denormal-input rescue (4 more instructions); callers pass values far from 1e-38
 __device__ __forceinline__ float rsq_approx(float x)

@@ -87,9 +87,12 @@ __device__ __forceinline__ float3 safe_inverse(float3 d)
 }
 
 // any_hit: the caller only needs "hit anything" (ambient_occlusion, main.c:104-106).
+// ray_scan = the part of a closest_hit query that needs no traversal state: the sphere scan, and whether the BVH has to be
+// walked at all (returns true) — false when there are no triangles, when an any-hit query is already answered by a sphere,
+// or when the ray misses the bounds of all triangles (or reaches them beyond the best sphere hit).
 template <bool HAS_TRIS, bool BRUTE, bool COUNT>
-__device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __restrict__ s_sph, float3 o, float3 d,
-                                          int src_prim, int src_twin, bool any_hit, Trav& tr, int* stack, TraceCounters& cnt)
+__device__ __forceinline__ bool ray_scan(const DevScene& sc, const float4* __restrict__ s_sph, float3 o, float3 d,
+                                         int src_prim, int src_twin, bool any_hit, Trav& tr, TraceCounters& cnt)
 {
     tr.t = __int_as_float(0x7f800000);
     tr.prim = TRT_NO_PRIM;
@@ -104,8 +107,8 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
         if (t >= 0.0f && t < tr.t) { tr.t = t; tr.prim = k; }
     }
     if (COUNT) cnt.sphere_tests += ns;
-    if (!HAS_TRIS || sc.n_tris == 0) return;
-    if (any_hit && tr.prim != TRT_NO_PRIM) return;
+    if (!HAS_TRIS || sc.n_tris == 0) return false;
+    if (any_hit && tr.prim != TRT_NO_PRIM) return false;
     if (BRUTE) {
         // linear scan like main.c:81-90 (leaf order; ties resolved by the caller's index)
         const int src_leaf = src_prim - ns;
@@ -120,23 +123,29 @@ __device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __re
                 if (take) { tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v; }
             }
         }
-        return;
+        return false;
     }
     // scene-box cull: a ray that misses the bounds of all triangles (or reaches them beyond the best
     // sphere hit) never enters the traversal loop
-    {
-        const float3 idir = safe_inverse(d);
-        const float ax = (sc.root_lo.x - o.x) * idir.x, bx = (sc.root_hi.x - o.x) * idir.x;
-        const float ay = (sc.root_lo.y - o.y) * idir.y, by = (sc.root_hi.y - o.y) * idir.y;
-        const float az = (sc.root_lo.z - o.z) * idir.z, bz = (sc.root_hi.z - o.z) * idir.z;
-        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));
-        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));
-        if (COUNT) cnt.box_tests += 1;
-        if (!(tf >= tn)) return;
+    const float3 idir = safe_inverse(d);
+    const float ax = (sc.root_lo.x - o.x) * idir.x, bx = (sc.root_hi.x - o.x) * idir.x;
+    const float ay = (sc.root_lo.y - o.y) * idir.y, by = (sc.root_hi.y - o.y) * idir.y;
+    const float az = (sc.root_lo.z - o.z) * idir.z, bz = (sc.root_hi.z - o.z) * idir.z;
+    const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));
+    const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));
+    if (COUNT) cnt.box_tests += 1;
+    return tf >= tn;
+}
+
+template <bool HAS_TRIS, bool BRUTE, bool COUNT>
+__device__ __forceinline__ void ray_begin(const DevScene& sc, const float4* __restrict__ s_sph, float3 o, float3 d,
+                                          int src_prim, int src_twin, bool any_hit, Trav& tr, int* stack, TraceCounters& cnt)
+{
+    if (ray_scan<HAS_TRIS, BRUTE, COUNT>(sc, s_sph, o, d, src_prim, src_twin, any_hit, tr, cnt)) {
+        stack[0] = TRT_TRAV_DONE;
+        tr.sp = 1;
+        tr.node = sc.root;
     }
-    stack[0] = TRT_TRAV_DONE;
-    tr.sp = 1;
-    tr.node = sc.root;
 }
 
 // Sphere-only scenes with ambient occlusion: the AO ray of bounce i and the bounce ray of bounce i+1 leave the same
@@ -213,7 +222,6 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
     if (!leaf) {
         ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b);
         ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
-        if (COUNT) cnt.box_tests += 4;
         const float INF = __int_as_float(0x7f800000);
 #define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
     {                                                                                                      \
@@ -223,6 +231,7 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
         const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));           \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
         KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
+        if (COUNT && REF != TRT_CHILD_EMPTY) cnt.box_tests++;                                               \
     }
         float k0, k1, k2, k3;
         int r0 = __float_as_int(f3a.x), r1 = __float_as_int(f3a.y), r2 = __float_as_int(f3a.z), r3 = __float_as_int(f3a.w);
@@ -276,7 +285,7 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
 template <bool COUNT>
 __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
                                                   int src_leaf, int twin_leaf, bool any_hit, int share,
-                                                  Trav& tr, int& pend, int* stack, TraceCounters& cnt)
+                                                  Trav& tr, int& pend, int* stack, TraceCounters& cnt, int exp_flags = 0)
 {
     if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) {
         const float4* rec = sc.nodes + 8 * (size_t)tr.node;
@@ -284,7 +293,6 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
         float4 f0a, f0b, f1a, f1b, f2a, f2b, f3a, f3b;
         ldg256(rec + 2 * ((0 + rot) & 3), f0a, f0b); ldg256(rec + 2 * ((1 + rot) & 3), f1a, f1b);
         ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b); ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
-        if (COUNT) cnt.box_tests += 4;
         const float INF = __int_as_float(0x7f800000);
 #define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
     {                                                                                                      \
@@ -294,6 +302,7 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
         const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));    \
         const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));           \
         KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
+        if (COUNT && REF != TRT_CHILD_EMPTY) cnt.box_tests++;                                               \
     }
         float k0, k1, k2, k3;
         int r0 = __float_as_int(f3a.x), r1 = __float_as_int(f3a.y), r2 = __float_as_int(f3a.z), r3 = __float_as_int(f3a.w);
@@ -312,7 +321,11 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
         if (k0 < INF) { tr.node = r0; tr.sp = sp; }
         else { tr.node = stack[sp - 1]; tr.sp = sp - 1; }
     }
-    if (tr.node < 0 && pend == 0) { pend = tr.node; tr.node = stack[--tr.sp]; }
+    if (tr.node < 0 && pend == 0) {
+        pend = tr.node; tr.node = stack[--tr.sp];
+        if (exp_flags & 1) prefetch_l1(sc.tri + 4 * (size_t)(~pend));
+    }
+    if ((exp_flags & 2) && tr.node >= 0 && tr.node != TRT_TRAV_DONE) prefetch_l1(sc.nodes + 8 * (size_t)tr.node);
     // the parked leaves are tested once a 1/share part of the lanes that are still inside hold one, or no lane can advance
     // (every one of them holds a leaf and has a second leaf or nothing in hand): a lane that is stuck WAITS for company
     // instead of forcing the triangle loop on the whole warp (same-call A/B on C2: 36.6 -> 35.3 ms)

@@ -17,6 +17,7 @@ struct RenderArgs {
     int bounces;            // nbRebondMax
     int use_ao;
     float inv_ao;           // 1 / AO_intensity
+    float sample_clamp;     // |per-sample value| bound before quantisation, see to_fixed
     float emit_scale_ao;    // 1.5 * AO_intensity
     float focus, aperture_x, aperture_y;
     float inv_wm1, inv_hm1; // 1/(W-1), 1/(H-1)
@@ -32,6 +33,13 @@ struct RenderArgs {
     int max_hk, hk_min;                 // megakernel: housekeeping passes per trip; repeated while fewer than hk_min/32 of the live lanes have BVH work
     int defer;                          // megakernel: > 0 = deferred leaves, tested once 1/defer of the lanes inside hold one (bvh_trip_deferred)
     int item_order;                     // see decode_item (trt_shade.cuh)
+    int exp_flags;                      // experiments (TRT_TUNE_EXP): 1 = L1 prefetch of a leaf's triangles when it is parked, 2 = of the next node after a visit
+    // slot-pool kernel (pathtrace_pool.cu): n_items = paths of this launch, pool = paths a warp reserves per atomic
+    int pp_slots;                       // path slots per warp (<= 64)
+    int pp_shade_at;                    // a shading pass starts once this many slots are hit-ready
+    int pp_refill_min;                  // lanes re-arm from the ray-ready ring once this many of the warp are idle
+    int pp_exit_below;                  // ... or the warp shades what it has when fewer rays than this are in flight or waiting
+    unsigned pp_per_tile, pp_m_per_tile, pp_m_spp; int pp_fit32;   // decode_path: 32 * spp and the reciprocals (fastdiv)
     int count_tests, wf_blocks, wf_check; // wavefront engine: count box/tri tests; trace CTAs per SM; waves between liveness checks
     long long n_items;
     unsigned long long* item_counter;   // zeroed before launch
@@ -67,6 +75,9 @@ void trt_wavefront_carve(void* base, int n_slots, WfState& S);
 cudaError_t trt_launch_wavefront(const RenderArgs& A, WfState& S, int n_sms, int* h_live_pinned, int* launches, cudaStream_t stream);
 
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream);
+// slot-pool kernel for triangle meshes (pathtrace_pool.cu); blocks_per_sm 0 = default
+cudaError_t trt_launch_pathtrace_pool(const RenderArgs& A, int n_sms, int blocks_per_sm, bool count_tests, cudaStream_t stream);
+size_t trt_pool_smem_bytes(const RenderArgs& A);
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
 cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, float* radiance, float* albedo, float* normal, int n_sms, cudaStream_t stream);
 

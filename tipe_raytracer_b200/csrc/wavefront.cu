@@ -73,9 +73,9 @@ wf_shade_kernel(const __grid_constant__ RenderArgs A, const __grid_constant__ Wf
         PathResult res;
         if (consume_hit(A, sc.sph, sc.sph_mat, pixel, s_cur, h.x, __float_as_int(h.y), h.z, h.w, P, phase, res)) {
             long long* a = S.acc + slot;
-            a[0 * (size_t)n] += to_fixed(res.L.x);      a[1 * (size_t)n] += to_fixed(res.L.y);      a[2 * (size_t)n] += to_fixed(res.L.z);
-            a[3 * (size_t)n] += to_fixed(res.albedo.x); a[4 * (size_t)n] += to_fixed(res.albedo.y); a[5 * (size_t)n] += to_fixed(res.albedo.z);
-            a[6 * (size_t)n] += to_fixed(res.normal.x); a[7 * (size_t)n] += to_fixed(res.normal.y); a[8 * (size_t)n] += to_fixed(res.normal.z);
+            a[0 * (size_t)n] += to_fixed(res.L.x, A.sample_clamp);      a[1 * (size_t)n] += to_fixed(res.L.y, A.sample_clamp);      a[2 * (size_t)n] += to_fixed(res.L.z, A.sample_clamp);
+            a[3 * (size_t)n] += to_fixed(res.albedo.x, A.sample_clamp); a[4 * (size_t)n] += to_fixed(res.albedo.y, A.sample_clamp); a[5 * (size_t)n] += to_fixed(res.albedo.z, A.sample_clamp);
+            a[6 * (size_t)n] += to_fixed(res.normal.x, A.sample_clamp); a[7 * (size_t)n] += to_fixed(res.normal.y, A.sample_clamp); a[8 * (size_t)n] += to_fixed(res.normal.z, A.sample_clamp);
             s_cur++;
             phase = PH_NEW;
         }
