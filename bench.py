@@ -13,8 +13,17 @@ AO off, emissive sky sphere.  A "step" renders every sample of every pixel of th
   e2e     the same metric through the reference-facing C ABI with HOST buffers: trt_scene_set (scene
           upload + GPU BVH build) + trt_render (trace, tonemap, 3 colour arrays copied back).
   N > 1   weak scaling: every rank renders `spp` samples of the full frame with a disjoint global sample
-          range (rank r: [r*spp, (r+1)*spp)), the int64 sums are reduced over NVLink with NCCL, rank 0
-          resolves the N*spp-sample image.
+          range (rank r: [r*spp, (r+1)*spp)), the int64 sums are reduced over NVLink with ncclReduce issued by
+          the C library itself (trt_reduce_nccl; torch.distributed only carries the rendezvous, the barriers and
+          the max-over-ranks of the timings), rank 0 resolves the N*spp-sample image.
+  also, on rank 0 (outside the timed region of `value`):
+          all_configs            N = 1: the other BASELINE configs (C1, C3, C4, C5) and the synthetic 1 M-triangle
+                                 C4big at FULL size: kernel ms, Mrays/s, roofline fraction;
+          strong_c5              BASELINE config 5 as written: the 1200x900x1000 spp frame split N ways
+                                 (trt_render_distributed: scene upload, trace, ncclReduce, resolve, D2H on rank 0),
+                                 efficiency against rank 0 rendering the whole frame alone;
+          bit_identical_vs_1gpu  rank 0 re-renders the N*spp frame alone and compares SHA-256 of canva / albedo /
+                                 normal with the NCCL-reduced image (north_star test 3 across GPU counts).
 
 --impl reference times the reference's own CPU implementation (oracle/_ref: /root/reference/main.c
 compiled as a library; pthread fan-out of main.c:402-453) on a bounded sample of the same workload.
@@ -47,6 +56,7 @@ def workload(name: str):
         "C3": "C3 nested dielectric spheres (refraction stack), 1000x750, 1000 spp, 19 bounces",
         "C4": "C4 1st_mc_world tree mesh (1792 tris, 1024^2 RGBA texture) + sky, 1920x1080, 500 spp, 6 bounces",
         "C5": "C5 README benchmark config 1200x900, 1000 spp, 6 bounces, AO on",
+        "C4big": "C4big SYNTHETIC: the C4 tree instanced 24x24 = 1 032 192 triangles + sky, 1920x1080, 6 bounces",
     }[name]
     return sc, desc
 
@@ -176,6 +186,51 @@ def run_reference_arm(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+def sha(res) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for k in ("canva", "albedo", "normal"):
+        h.update(np.ascontiguousarray(res[k]).tobytes())
+    return h.hexdigest()
+
+
+def fp32_peak_tflops(torch, dev):
+    peaks, peak_src = measured_peaks()
+    sm_clock = (peaks.get("sm_max_mhz") or 1965.0) * 1e6
+    n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+    return n_sm * 128 * 2 * sm_clock / 1e12, n_sm, sm_clock, peaks, peak_src
+
+
+def config_on_device(torch, trt, S, r, name, dev, spp_override=None):
+    """One BASELINE config at full size on this GPU, scene resident: kernel ms (CUDA events around the launch, inside
+    the library), rays, and the FP32 intersection roofline with MEASURED tests per ray."""
+    sc, desc = workload(name)
+    spp = spp_override or sc.spp
+    r.scene_set(sc)
+    rp = S.params_for(sc, spp=spp)
+    npix = rp.width * rp.height
+    acc = torch.zeros(9 * npix, dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    r.accumulate(S.params_for(sc, spp=max(1, spp // 10)), acc.data_ptr())          # warm-up: a tenth of the samples
+    best, st = None, None
+    for _ in range(2 if name in ("C1", "C2") else 1):
+        acc.zero_(); torch.cuda.synchronize()
+        st = r.accumulate(rp, acc.data_ptr())
+        best = st["ms_trace"] if best is None else min(best, st["ms_trace"])
+    acc.zero_(); torch.cuda.synchronize()
+    cst = r.accumulate(S.params_for(sc, spp=min(spp, 16), flags=trt.FLAG_COUNT_TESTS), acc.data_ptr())
+    n_box, n_tri, n_sph = (cst[k] / max(cst["rays"], 1) for k in ("box_tests", "tri_tests", "sphere_tests"))
+    f_ray = n_box * 18 + n_tri * 55 + n_sph * 25 + 29
+    peak = fp32_peak_tflops(torch, dev)[0]
+    achieved = st["rays"] * f_ray / (best * 1e-3) / 1e12
+    del acc
+    return {"workload": desc, "width": rp.width, "height": rp.height, "spp": spp, "nbRebondMax": rp.bounces, "useAO": bool(sc.use_ao),
+            "kernel_ms": best, "rays": st["rays"], "rays_per_path": st["rays"] / st["paths"], "mrays_s": st["rays"] / best / 1e3,
+            "nominal_mrays_s": npix * spp * rp.bounces / best / 1e3, "msamples_s": npix * spp / best / 1e3,
+            "flops_per_ray": f_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri, "sphere_tests_per_ray": n_sph,
+            "roofline_frac": achieved / peak, "bvh": r.bvh_info() if sc.triangles.shape[0] else None}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,6 +240,7 @@ def main():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (debug)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip all_configs / strong_c5 / bit_identical_vs_1gpu")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -225,6 +281,14 @@ def main():
     out_dev = torch.zeros(9 * npix, dtype=torch.float64, device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
 
+    # the data-path collective is the library's own ncclReduce (trt_reduce_nccl): its communicator is made from an id
+    # rank 0 draws and torch.distributed hands round (plumbing)
+    comm = 0
+    if world > 1:
+        box = [r.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = r.nccl_comm_init(world, rank, box[0])
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -236,8 +300,7 @@ def main():
             accum.zero_()
         st = r.accumulate(rp, accum.data_ptr())
         if world > 1:
-            with torch.cuda.stream(ext):
-                D.reduce_accum(accum, dst=0)                       # int64 SUM over NVLink (NCCL)
+            r.reduce_nccl(comm, accum.data_ptr(), 9 * npix, 0)          # int64 SUM over NVLink, on the library's stream
             if rank == 0:
                 r.resolve_device(rp, accum.data_ptr(), out_dev.data_ptr(), out_dev.data_ptr() + 24 * npix, out_dev.data_ptr() + 48 * npix)
         return st
@@ -277,27 +340,20 @@ def main():
     host = dict(canva=np.empty((npix, 3)), albedo=np.empty((npix, 3)), normal=np.empty((npix, 3)))
     h2d = int(sc.spheres.nbytes + sc.triangles.nbytes + sc.mat_list.nbytes + sc.quel_mat_pour_tri.nbytes)
     d2h = 3 * npix * 24
-
-    e2e_parts = {"scene_set_ms": 0.0, "render_ms": 0.0}
+    e2e_parts = {"scene_set_ms": 0.0}
+    rp_job = S.params_for(sc, spp=spp * world)                # the N*spp-sample frame; every rank takes its N-th of the samples
 
     def step_e2e():
         t0 = time.perf_counter()
         r.scene_set(sc)                                   # H2D of the reference-layout arrays + BVH build
         e2e_parts["scene_set_ms"] += (time.perf_counter() - t0) * 1e3
         if world == 1:
-            return r.render(S.params_for(sc, spp=spp), out=host)["stats"]      # trace + resolve + D2H
-        with torch.cuda.stream(ext):
-            accum.zero_()
-        st = r.accumulate(rp, accum.data_ptr())
-        with torch.cuda.stream(ext):
-            D.reduce_accum(accum, dst=0)
-        if rank == 0:
-            r.resolve(rp, accum.data_ptr(), out=host)       # same caller-owned host arrays every step, like the N=1 leg
-        return st
+            return r.render(rp_job, out=host)["stats"]      # trt_render: trace + resolve + D2H
+        return r.render_distributed(rp_job, comm, rank, world, out=host if rank == 0 else None)["stats"]   # + ncclReduce
 
-    step_e2e()
-    e2e_parts = {"scene_set_ms": 0.0, "render_ms": 0.0}
-    e2e_steps = max(2, min(steps, 3))
+    step_e2e(); step_e2e()
+    e2e_parts["scene_set_ms"] = 0.0
+    e2e_steps = max(10, steps)
     t0 = time.perf_counter()
     te_ms, est = timed(step_e2e, e2e_steps)
     e2e_wall = time.perf_counter() - t0
@@ -308,6 +364,65 @@ def main():
         b = te.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
         te_ms, e_rays = float(a[0]), float(b[1])
     e2e_value = e_rays / (te_ms * 1e-3) / 1e6
+    e2e_hash = sha(host) if rank == 0 else None
+
+    # ---- extras (outside the timed regions above) -------------------------------------------------------
+    extras = {}
+    if not args.no_extras:
+        # north_star test 3: the image of N GPUs (NCCL-reduced, above) against ONE GPU rendering all N*spp samples
+        if world > 1:
+            if rank == 0:
+                alone = r.render(rp_job)
+                extras["bit_identical_vs_1gpu"] = {"weak_" + args.config: bool(sha(alone) == e2e_hash), "spp_total": spp * world,
+                                                   "sha256_n_gpus": e2e_hash, "sha256_1_gpu": sha(alone)}
+            barrier()
+        # BASELINE config 5 as written: strong scaling of the 1200x900x1000 spp frame
+        sc5, desc5 = workload("C5")
+        rp5 = S.params_for(sc5)
+        n5 = rp5.width * rp5.height
+        host5 = dict(canva=np.empty((n5, 3)), albedo=np.empty((n5, 3)), normal=np.empty((n5, 3))) if rank == 0 else None
+
+        def step_c5():
+            r.scene_set(sc5)
+            if world == 1:
+                return r.render(rp5, out=host5)["stats"]
+            return r.render_distributed(rp5, comm, rank, world, out=host5)["stats"]
+
+        step_c5()                                          # warm-up: buffers of this size, pinned staging
+        c5_steps = 3
+        t5_ms, st5 = timed(step_c5, c5_steps)
+        t5 = torch.tensor([t5_ms, float(sum(s["rays"] for s in st5)), float(max(s["ms_trace"] for s in st5))], dtype=torch.float64, device=dev)
+        if world > 1:
+            a = t5.clone(); dist.all_reduce(a, op=dist.ReduceOp.MAX)
+            b = t5.clone(); dist.all_reduce(b, op=dist.ReduceOp.SUM)
+            t5_ms, rays5, trace5 = float(a[0]), float(b[1]), float(a[2])
+        else:
+            rays5, trace5 = float(t5[1]), float(t5[2])
+        strong = {"workload": desc5, "n_gpus": world, "steps": c5_steps, "ms_per_frame": t5_ms / c5_steps, "trace_ms_max_rank": trace5,
+                  "mrays_s": rays5 / (t5_ms * 1e-3) / 1e6, "msamples_s": n5 * rp5.spp * c5_steps / (t5_ms * 1e-3) / 1e6,
+                  "what": "trt_scene_set + trt_render_distributed (trace of spp/N, ncclReduce int64, resolve, D2H on rank 0), host buffers, max over ranks"}
+        if world > 1:
+            if rank == 0:
+                h_n = sha(host5)
+                t0 = time.perf_counter()
+                r.scene_set(sc5); alone5 = r.render(rp5, out=host5)        # the whole frame on rank 0 alone, same call sequence
+                one_ms = (time.perf_counter() - t0) * 1e3
+                strong["ms_per_frame_1gpu_same_box"] = one_ms
+                strong["efficiency_vs_1gpu"] = one_ms / (world * t5_ms / c5_steps)
+                extras.setdefault("bit_identical_vs_1gpu", {})["strong_C5"] = bool(sha(alone5) == h_n)
+            barrier()
+        extras["strong_c5"] = strong
+        del host5
+        # every other BASELINE config at full size, N = 1 (scene resident, kernel-timed)
+        if world == 1:
+            allc = {}
+            for name, spp_o in (("C1", None), ("C3", None), ("C4", None), ("C5", None), ("C4big", 100)):
+                try:
+                    allc[name] = config_on_device(torch, trt, S, r, name, dev, spp_o)
+                except Exception as e:           # a config that fails must not take the headline line with it
+                    allc[name] = {"error": str(e)[:200]}
+            extras["all_configs"] = allc
+            r.scene_set(sc)                      # back to the headline workload for the roofline pass below
 
     if rank == 0:
         # ---- roofline of the dominant kernel (pathtrace_kernel): measured tests per ray x FLOPs per test
@@ -317,16 +432,14 @@ def main():
         n_box, n_tri, n_sph = (cst[k] / max(cst["rays"], 1) for k in ("box_tests", "tri_tests", "sphere_tests"))
         f_ray = n_box * 18 + n_tri * 55 + n_sph * 25 + 29
         rays_per_launch = rays_local / steps
-        peaks, peak_src = measured_peaks()
-        sm_clock = (peaks.get("sm_max_mhz") or 1965.0) * 1e6
-        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
-        fp32_peak = n_sm * 128 * 2 * sm_clock / 1e12                 # TFLOP/s
+        fp32_peak, n_sm, sm_clock, peaks, peak_src = fp32_peak_tflops(torch, dev)
         achieved = rays_per_launch * f_ray / (kernel_ms * 1e-3) / 1e12
         chunk = max(4, min(16, (spp + 10) // 20)) if sc.triangles.shape[0] > 0 else 16      # samples per item (api.cu)
         hbm_alg = 9 * 8 * npix * ((spp + chunk - 1) // chunk)       # int64 RED traffic of the item flushes, per launch
         traffic = None
         try:        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, from the committed ncu capture
-            with open(os.path.join(ROOT, "profiles", "r01_traffic_c2.json")) as f:
+            cand = [os.path.join(ROOT, "profiles", n) for n in ("r02_traffic_c2.json", "r01_traffic_c2.json")]
+            with open(next(c for c in cand if os.path.exists(c))) as f:
                 tj = json.load(f)
             if args.config == "C2" and spp == sc.spp:
                 traffic = {"bytes_per_launch": tj["traffic_bytes_per_launch"], "source": tj["source"]}
@@ -337,6 +450,7 @@ def main():
             "frac": achieved / fp32_peak, "traffic": traffic,
             "peak_source": f"{n_sm} SMs x 128 FP32 lanes x 2 x {sm_clock/1e6:.0f} MHz (sm_max_mhz from MEASURED_PEAKS.json, {peak_src})",
             "flops_per_ray": f_ray, "box_tests_per_ray": n_box, "tri_tests_per_ray": n_tri, "sphere_tests_per_ray": n_sph,
+            "box_tests_note": "child boxes actually tested: empty slots of the 4-wide nodes are not counted",
             "rays_per_launch": rays_per_launch, "kernel_ms": kernel_ms,
             "hbm": {"algorithmic_bytes_per_launch": hbm_alg, "achieved_gbs": hbm_alg / (kernel_ms * 1e-3) / 1e9,
                     "peak_gbs": peaks.get("hbm_gbs"), "note": "working set (BVH+triangles+texels) is L2-resident; HBM is not the limiter"},
@@ -352,7 +466,7 @@ def main():
             "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp * world,
                        "nbRebondMax": sc.bounces, "useAO": bool(sc.use_ao), "seed": rp.seed,
                        "l2": "512 MB buffer written between timed steps (L2 flush)",
-                       "parallelism": f"spp-split x{world}, int64 NCCL reduce" if world > 1 else "single GPU"},
+                       "parallelism": f"spp-split x{world}, int64 ncclReduce issued by libtipe_rt (trt_reduce_nccl)" if world > 1 else "single GPU"},
             "rays_per_step": rays_total / steps, "rays_per_path": rays_local / steps / (npix * spp),
             "nominal_mrays_s": npix * spp * world * sc.bounces / (ms_per_step * 1e-3) / 1e6,
             "msamples_s": npix * spp * world / (ms_per_step * 1e-3) / 1e6,
@@ -360,13 +474,17 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": te_ms / e2e_steps, "steps": e2e_steps, "wall_s": e2e_wall,
                     "scene_set_ms_per_step": e2e_parts["scene_set_ms"] / e2e_steps,
-                    "what": "trt_scene_set (upload + GPU BVH build) + trt_render into host color arrays"},
+                    "what": ("trt_scene_set (upload + GPU BVH build) + trt_render into host color arrays" if world == 1 else
+                             "trt_scene_set + trt_render_distributed (N*spp samples split over the ranks, ncclReduce, resolve, D2H on rank 0)")},
             "roofline": roofline, "bvh": r.bvh_info(),
         }
+        line.update(extras)
         if cpu:
             line["cpu_baseline"] = cpu
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
+    if comm:
+        r.nccl_comm_destroy(comm)
     r.close()
     if world > 1:
         dist.destroy_process_group()

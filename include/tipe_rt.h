@@ -168,6 +168,11 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
 TRT_API int trt_primary(trt_ctx* ctx, const trt_params* params,
                         double* t, int* id, trt_vec3* normal, trt_vec3* albedo);
 
+/* The same pixel-centre rays through the arithmetic trt_render actually uses: FP32 camera ray, FP32 sphere / triangle tests, the
+ * BVH walk.  Not bit-exact against the FP64 pass by construction (a ray through a silhouette may fall on the other side); the
+ * tests measure how often.  t in units of |d| (float), id in the caller's numbering.  Either output may be NULL. */
+TRT_API int trt_primary_fp32(trt_ctx* ctx, const trt_params* params, float* t, int* id);
+
 /* ---- device-resident pieces (what trt_render is made of; used by the multi-process path
  *      where the sample sums cross GPUs with an NCCL reduce, and by bench.py) -------------- */
 #define TRT_ACCUM_CHANNELS 9      /* radiance rgb, albedo rgb, normal xyz */
@@ -188,6 +193,32 @@ TRT_API int trt_resolve_device(trt_ctx* ctx, const trt_params* params, const int
  * trip of denoiser.h:43-45. The denoiser itself (denoiser.h:31-91) stays outside this library. */
 TRT_API int trt_resolve_hdr(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
                             float* radiance, float* albedo, float* normal);
+/* Same, into DEVICE buffers on the ctx's first device (3*W*H floats each): what a GPU denoiser build (oidnNewSharedBuffer on
+ * device memory; denoiser.h:41-59 fills host arrays) consumes without the frame ever leaving HBM.  Returns when the buffers are ready. */
+TRT_API int trt_resolve_hdr_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                                   float* d_radiance, float* d_albedo, float* d_normal);
+
+/* ---- the collective of the multi-process path (one process per GPU; SURVEY §8e, BASELINE config 5) -------------------
+ * Every rank renders its sample range with trt_accumulate, then trt_reduce_nccl adds the int64 sums of all ranks onto
+ * `root` (root < 0: onto every rank, ncclAllReduce) with ncclReduce(ncclInt64, ncclSum) on the ctx's stream, and the root
+ * calls trt_resolve.  Asynchronous like NCCL itself: ordered with the ctx's other work, complete after trt_synchronize or
+ * the next blocking call.  `comm` is an ncclComm_t: the caller's own, or one made by trt_nccl_comm_init from a 128-byte
+ * ncclUniqueId that rank 0 obtained with trt_nccl_unique_id and handed to the other ranks by any means (file, socket,
+ * MPI).  NCCL is loaded at run time (libnccl.so.2); the reference has no counterpart (pthreads, main.c:402-453). */
+#define TRT_NCCL_UNIQUE_ID_BYTES 128
+TRT_API int trt_nccl_version(void);                           /* 0 when NCCL cannot be loaded */
+TRT_API int trt_nccl_unique_id(void* out128);
+TRT_API int trt_nccl_comm_init(trt_ctx* ctx, int n_ranks, int rank, const void* unique_id128, void** comm_out);
+TRT_API int trt_nccl_comm_destroy(void* comm);
+TRT_API int trt_reduce_nccl(trt_ctx* ctx, void* comm, int64_t* d_accum, size_t count, int root);
+/* The drop-in call for ONE PROCESS PER GPU: every rank calls it with the same params; rank r traces the samples
+ * [r*spp/N, (r+1)*spp/N) of every pixel (or, with TRT_FLAG_TILE_SPLIT, all samples of the tiles r mod N), the sums meet on
+ * rank 0 through trt_reduce_nccl, rank 0 tonemaps into canva / albedo_tab / normal_tab (ignored on the other ranks, may be
+ * NULL there).  The image is bit-identical to trt_render on one GPU.  stats describe this rank's share. */
+TRT_API int trt_render_distributed(trt_ctx* ctx, const trt_params* params, void* nccl_comm, int rank, int n_ranks,
+                                   trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats);
+/* CUDA ordinal of the ctx's k-th device (-1 if out of range) */
+TRT_API int trt_device_of(const trt_ctx* ctx, int k);
 
 /* Stream the ctx's first device works on (a cudaStream_t), for callers that interleave their own work. */
 TRT_API void* trt_stream(trt_ctx* ctx);
@@ -229,6 +260,7 @@ TRT_STATIC_ASSERT(sizeof(trt_camera) == 96, "camera layout (camera.h:10-15)");
 #define TRT_ERR_CUDA          -3
 #define TRT_ERR_NO_SCENE      -4
 #define TRT_ERR_OOM           -5
+#define TRT_ERR_NCCL          -6
 
 #ifdef __cplusplus
 }

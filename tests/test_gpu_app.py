@@ -108,20 +108,27 @@ def test_fill_canva_thread_data_mirror(rt):
     assert np.array_equal(band["canva"][lo:hi], want["canva"][lo:hi]) and not band["canva"][:lo].any() and not band["canva"][hi:].any()
 
 
-def test_wavefront_engine_is_bit_identical_to_the_megakernel(rt):
+def test_slot_pool_kernel_is_bit_identical_to_the_register_kernel(rt):
+    """pathtrace.cu (engine 1, a lane owns a path) and pathtrace_pool.cu (engine 3, a warp owns 64 path slots in shared memory): same image."""
     sc = S.nature_mesh()
     rt.scene_set(sc)
     rp = S.params_for(sc, width=200, spp=12)
     try:
         os.environ["TRT_ENGINE"] = "1"
         a = rt.render(rp)
-        os.environ["TRT_ENGINE"] = "2"
+        os.environ["TRT_ENGINE"] = "3"
         b = rt.render(rp)
+        sc2 = S.nature_mesh(); sc2.use_ao = True                         # AO rays: the parked bounce direction of the slot record
+        rt.scene_set(sc2)
+        rp2 = S.params_for(sc2, width=97, spp=5)
+        d = rt.render(rp2)
+        os.environ["TRT_ENGINE"] = "1"
+        c = rt.render(rp2)
     finally:
         os.environ.pop("TRT_ENGINE", None)
     for k in ("canva", "albedo", "normal"):
-        assert a[k].tobytes() == b[k].tobytes()
-    assert a["stats"]["rays"] == b["stats"]["rays"] and b["stats"]["kernel_launches"] > 3
+        assert a[k].tobytes() == b[k].tobytes() and c[k].tobytes() == d[k].tobytes()
+    assert a["stats"]["rays"] == b["stats"]["rays"] and c["stats"]["rays"] == d["stats"]["rays"]
 
 
 def test_in_process_multi_gpu_is_bit_identical():

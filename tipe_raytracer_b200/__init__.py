@@ -28,7 +28,8 @@ ACCUM_CHANNELS, ACCUM_FRAC_BITS = 9, 28
 # every symbol include/tipe_rt.h declares
 ABI_SYMBOLS = [
     "trt_default_overrides", "trt_init", "trt_destroy", "trt_last_error", "trt_version",
-    "trt_scene_set", "trt_sky_set", "trt_render", "trt_primary", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr",
+    "trt_scene_set", "trt_sky_set", "trt_render", "trt_primary", "trt_primary_fp32", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr", "trt_resolve_hdr_device",
+    "trt_nccl_version", "trt_nccl_unique_id", "trt_nccl_comm_init", "trt_nccl_comm_destroy", "trt_reduce_nccl", "trt_device_of", "trt_render_distributed",
     "trt_stream", "trt_synchronize", "trt_bvh_info_get", "trt_debug_schedule",
     "trt_kat_hit_sphere", "trt_kat_hit_triangle", "trt_kat_refract", "trt_kat_philox", "trt_kat_tonemap",
 ]
@@ -191,6 +192,14 @@ class Renderer:
         self._check(self.lib.trt_primary(self.ctx, C.byref(p), _ptr(t), _ptr(ids), _ptr(normal), _ptr(albedo)), "trt_primary")
         return dict(t=t, id=ids, normal=normal, albedo=albedo)
 
+    def primary_fp32(self, rp: RenderParams) -> dict:
+        """First hit of the pixel-centre rays through the path tracer's own FP32 / BVH arithmetic."""
+        n = rp.width * rp.height
+        t = np.empty(n, np.float32); ids = np.empty(n, np.int32)
+        p = make_params(rp)
+        self._check(self.lib.trt_primary_fp32(self.ctx, C.byref(p), _ptr(t), _ptr(ids)), "trt_primary_fp32")
+        return dict(t=t, id=ids)
+
     # -- device-resident pieces ------------------------------------------------------------------
     def accumulate(self, rp: RenderParams, d_accum_ptr: int) -> dict:
         """Adds rp.spp samples starting at rp.sample_offset into the int64 [9][H*W] device buffer."""
@@ -216,10 +225,52 @@ class Renderer:
         self._check(self.lib.trt_resolve_hdr(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), _ptr(rad), _ptr(alb), _ptr(nrm)), "trt_resolve_hdr")
         return dict(radiance=rad, albedo=alb, normal=nrm)
 
+    def resolve_hdr_device(self, rp: RenderParams, d_accum_ptr: int, d_radiance: int, d_albedo: int, d_normal: int):
+        """Float32 means into device buffers (3*W*H floats each), for a denoiser that reads device memory."""
+        p = make_params(rp)
+        self._check(self.lib.trt_resolve_hdr_device(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(d_radiance),
+                                                    C.c_void_p(d_albedo), C.c_void_p(d_normal)), "trt_resolve_hdr_device")
+
     def resolve_device(self, rp: RenderParams, d_accum_ptr: int, d_canva: int, d_albedo: int, d_normal: int):
         p = make_params(rp)
         self._check(self.lib.trt_resolve_device(self.ctx, C.byref(p), C.c_void_p(d_accum_ptr), C.c_void_p(d_canva),
                                                 C.c_void_p(d_albedo), C.c_void_p(d_normal)), "trt_resolve_device")
+
+    # -- one process per GPU: NCCL inside the library (nccl_glue.cu) ----------------------------------
+    def nccl_unique_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = self.lib.trt_nccl_unique_id(buf)
+        if rc != 0:
+            msg = self.lib.trt_last_error(None)
+            raise TrtError(f"trt_nccl_unique_id failed ({rc}): {msg.decode() if msg else ''}")
+        return buf.raw
+
+    def nccl_comm_init(self, n_ranks: int, rank: int, unique_id: bytes) -> int:
+        comm = C.c_void_p()
+        self._check(self.lib.trt_nccl_comm_init(self.ctx, C.c_int(n_ranks), C.c_int(rank), C.c_char_p(unique_id), C.byref(comm)), "trt_nccl_comm_init")
+        return int(comm.value or 0)
+
+    def nccl_comm_destroy(self, comm: int):
+        self.lib.trt_nccl_comm_destroy(C.c_void_p(comm))
+
+    def reduce_nccl(self, comm: int, d_accum_ptr: int, count: int, root: int = 0):
+        """ncclReduce(int64, SUM) of the sample sums onto `root` (root < 0: all-reduce), asynchronous on the ctx's stream."""
+        self._check(self.lib.trt_reduce_nccl(self.ctx, C.c_void_p(comm), C.c_void_p(d_accum_ptr), C.c_size_t(count), C.c_int(root)), "trt_reduce_nccl")
+
+    def render_distributed(self, rp: RenderParams, comm: int, rank: int, n_ranks: int, out: Optional[dict] = None) -> dict:
+        """trt_render_distributed: this rank's share of rp.spp, NCCL reduce, rank 0 gets the image (other ranks: stats only)."""
+        n = rp.width * rp.height
+        res = {}
+        if rank == 0:
+            res = dict(canva=out["canva"] if out else np.empty((n, 3)), albedo=out["albedo"] if out else np.empty((n, 3)),
+                       normal=out["normal"] if out else np.empty((n, 3)))
+        p = make_params(rp)
+        st = TrtStats()
+        self._check(self.lib.trt_render_distributed(self.ctx, C.byref(p), C.c_void_p(comm), C.c_int(rank), C.c_int(n_ranks),
+                                                    _ptr(res.get("canva")), _ptr(res.get("albedo")), _ptr(res.get("normal")), C.byref(st)),
+                    "trt_render_distributed")
+        res["stats"] = st.as_dict()
+        return res
 
     def debug_schedule(self) -> dict:
         out = (C.c_uint64 * 7)()

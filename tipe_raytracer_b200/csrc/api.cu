@@ -46,7 +46,6 @@ struct DeviceCtx {
     unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
     unsigned long long* h_ctrs = nullptr;      // pinned mirror
     long long* accum = nullptr; size_t accum_px = 0;
-    void* wf_buf = nullptr; size_t wf_bytes = 0;   // wavefront slot state
     int last_launches = 0;
     double* out = nullptr; size_t out_px = 0;  // canva | albedo | normal, each [npix][3]
     // device -> caller copy: pinned staging + one event per chunk, so that host threads can move finished chunks into the
@@ -57,11 +56,23 @@ struct DeviceCtx {
 
 }  // namespace
 
+// Pinned ring for large host -> device uploads (texture slabs, big meshes): host threads pack / copy chunks into the ring
+// while the DMA engine ships the previous ones, instead of one pageable cudaMemcpy the driver stages at a few GB/s.
+struct UploadRing {
+    char* h = nullptr;
+    size_t chunk = (size_t)1 << 20;
+    int slots = 8;
+    cudaEvent_t ev[8] = {};
+    cudaEvent_t done = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
 struct trt_ctx {
     std::vector<DeviceCtx> devs;
     std::string err;
     bool has_scene = false;
     trt_bvh_info info{};
+    UploadRing ring;            // on devs[0]
 };
 
 namespace {
@@ -176,6 +187,58 @@ int copy_out(trt_ctx* ctx, DeviceCtx& d, size_t npix, trt_vec3* canva, trt_vec3*
     return TRT_OK;
 }
 
+cudaError_t ensure_ring(trt_ctx* ctx)
+{
+    UploadRing& r = ctx->ring;
+    if (r.h) return cudaSuccess;
+    cudaError_t e = cudaHostAlloc((void**)&r.h, r.chunk * r.slots, cudaHostAllocDefault);
+    if (e != cudaSuccess) { r.h = nullptr; return e; }
+    if ((e = cudaStreamCreateWithFlags(&r.stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int k = 0; k < r.slots; k++) if ((e = cudaEventCreateWithFlags(&r.ev[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+    return cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming);
+}
+
+// n items of in_bytes each at `src` (host, pageable) -> n items of out_bytes each at `dst` on devs[0], through pack(dst_chunk,
+// src_chunk, count) run by host threads into the pinned ring.  d.stream waits for the last chunk; the call returns when every
+// chunk has been packed (the caller's array may be freed), not when the copies have landed.
+template <class Pack>
+int staged_upload(trt_ctx* ctx, char* dst, const char* src, size_t n, size_t in_bytes, size_t out_bytes, Pack pack)
+{
+    DeviceCtx& d = ctx->devs[0];
+    CU(ctx, ensure_ring(ctx));
+    UploadRing& r = ctx->ring;
+    const size_t per_chunk = r.chunk / out_bytes, n_chunks = (n + per_chunk - 1) / per_chunk;
+    int n_threads = 8;                                   // a power of two that divides r.slots: chunk c and chunk c - slots belong to the same thread
+    { const unsigned hc = std::thread::hardware_concurrency(); while (n_threads > 1 && (hc > 0 && (unsigned)n_threads > hc)) n_threads >>= 1; }
+    while (n_threads > 1 && (size_t)n_threads > n_chunks) n_threads >>= 1;
+    cudaError_t errs[8];
+    auto worker = [&](int t) {
+        errs[t] = cudaSetDevice(d.dev);
+        for (size_t c = (size_t)t; c < n_chunks && errs[t] == cudaSuccess; c += (size_t)n_threads) {
+            const int slot = (int)(c % (size_t)r.slots);
+            if (c >= (size_t)r.slots) errs[t] = cudaEventSynchronize(r.ev[slot]);           // the slot's previous copy has left the ring
+            if (errs[t] != cudaSuccess) break;
+            const size_t first = c * per_chunk, count = (first + per_chunk <= n) ? per_chunk : n - first;
+            char* h = r.h + (size_t)slot * r.chunk;
+            pack(h, src + first * in_bytes, count);
+            errs[t] = cudaMemcpyAsync(dst + first * out_bytes, h, count * out_bytes, cudaMemcpyHostToDevice, r.stream);
+            if (errs[t] == cudaSuccess) errs[t] = cudaEventRecord(r.ev[slot], r.stream);
+        }
+    };
+    std::thread th[7];
+    for (int t = 1; t < n_threads; t++) th[t - 1] = std::thread(worker, t);
+    worker(0);
+    for (int t = 1; t < n_threads; t++) th[t - 1].join();
+    for (int t = 0; t < n_threads; t++) CU(ctx, errs[t]);
+    CU(ctx, cudaEventRecord(r.done, r.stream));
+    CU(ctx, cudaStreamWaitEvent(d.stream, r.done, 0));
+    // the ring is reused by the next upload: its chunks must have left before that one overwrites them
+    CU(ctx, cudaEventSynchronize(r.done));
+    return TRT_OK;
+}
+
+const size_t STAGED_MIN_BYTES = (size_t)4 << 20;        // below this a plain cudaMemcpyAsync is as fast
+
 int check_params(trt_ctx* ctx, const trt_params* p)
 {
     if (!ctx) return TRT_ERR_INVALID;
@@ -203,13 +266,12 @@ int check_params(trt_ctx* ctx, const trt_params* p)
 }
 
 // Launches K2 for `spp` samples starting at global sample `offset` into `accum` on device d.
-int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int offset, long long* accum, int tile_offset = 0, int tile_stride = 1)
+// scene, image size, camera and the per-frame constants of RenderArgs (shared by the path tracer and trt_primary_fp32)
+void fill_camera_args(RenderArgs& A, DeviceCtx& d, const trt_params* p)
 {
-    RenderArgs A{};
     A.scene = d.scene;
     { const char* v = getenv("TRT_TUNE_BOXTMIN"); A.scene.box_tmin = (v && *v && atoi(v) == 0) ? 0.0f : d.scene.tri_tmin; }
     A.W = p->largeur_image; A.H = p->hauteur_image;
-    A.spp = spp; A.sample_offset = offset;
     A.bounces = p->nbRebondMax;
     A.use_ao = p->useAO ? 1 : 0;
     A.inv_ao = (float)(1.0 / p->AO_intensity);
@@ -228,16 +290,20 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.cam_corner = make_float3((float)(c.coin_bas_gauche.e[0] - c.origin.e[0]), (float)(c.coin_bas_gauche.e[1] - c.origin.e[1]),
                                (float)(c.coin_bas_gauche.e[2] - c.origin.e[2]));
     A.key0 = (uint32_t)(p->seed & 0xffffffffu); A.key1 = (uint32_t)(p->seed >> 32);
+}
+
+int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int offset, long long* accum, int tile_offset = 0, int tile_stride = 1)
+{
+    RenderArgs A{};
+    fill_camera_args(A, d, p);
+    A.spp = spp; A.sample_offset = offset;
     // tuning knobs (defaults chosen from measurements on B200); env overrides are for experiments
     auto knob = [](const char* name, int dflt) { const char* v = getenv(name); return v && *v ? atoi(v) : dflt; };
     const bool brute = (p->flags & TRT_FLAG_BRUTE_FORCE) != 0, count_tests = (p->flags & TRT_FLAG_COUNT_TESTS) != 0;
-    // engine 1 = register-resident megakernel (default), 2 = wavefront (opt-in, TRT_ENGINE=2)
-    int engine = knob("TRT_ENGINE", 0);
-    if (engine == 0) engine = 1;    // measured on B200: the megakernel wins on every reference scene; the wavefront engine is opt-in
-    if (engine == 2 && (brute || p->nbRebondMax > 8191)) engine = 1;
-    const int chunk_max = engine == 2 ? knob("TRT_TUNE_WF_CHUNK", 16) : knob("TRT_TUNE_CHUNK", 16);
-    A.min_steps = knob("TRT_TUNE_MIN_STEPS", engine == 2 ? 4 : 2);
-    A.exit_num = knob("TRT_TUNE_EXIT", engine == 2 ? 24 : 10);
+    // engine 1 = register-resident megakernel (default), 3 = slot-pool kernel for meshes (opt-in, TRT_ENGINE=3)
+    const int chunk_max = knob("TRT_TUNE_CHUNK", 16);
+    A.min_steps = knob("TRT_TUNE_MIN_STEPS", 2);
+    A.exit_num = knob("TRT_TUNE_EXIT", 10);
     // sphere scenes: the lanes of a warp start their next paths TOGETHER, once none of them has a path left (32 = all): closed
     // scenes give paths of similar length, and lanes that stay in step share the bounce index, the AO / bounce phase and most
     // branches (C1 16.4 -> 12.5 ms, C5 -24 %, C3 -18 %); meshes: every lane re-arms on its own (paths of 1-4 rays)
@@ -248,11 +314,9 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.exp_flags = knob("TRT_TUNE_EXP", 0);
     A.item_order = knob("TRT_TUNE_ORDER", d.scene.n_tris > 0 ? 1 : 0);   // meshes: a warp starts on the samples of 2-3 neighbouring pixels (coherent primary rays, +2-3 %); spheres: one tile (+5 %)
     A.count_tests = count_tests ? 1 : 0;
-    A.wf_blocks = knob("TRT_TUNE_WF_BLOCKS", 0);
-    A.wf_check = knob("TRT_TUNE_WF_CHECK", 8);
     const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (4 CTAs of 256 threads per SM, 64 registers)
     A.chunk = spp < chunk_max ? spp : chunk_max;
-    if (engine != 2 && d.scene.n_tris > 0 && !getenv("TRT_TUNE_CHUNK")) {
+    if (d.scene.n_tris > 0 && !getenv("TRT_TUNE_CHUNK")) {
         // meshes (chunk-fastest item order): about 20 chunks per pixel, so that the 32 items a warp reserves are the chunks of
         // one or two pixels — near-identical primary rays — while an item still amortises its flush (C2, 200 spp: chunk 10
         // 33.5 ms vs chunk 16 35.3 ms; 20 spp: chunk 4 7.3 ms vs 10.7 ms)
@@ -307,23 +371,6 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
         CU(ctx, trt_launch_pathtrace_pool(A, d.n_sms, blocks_per_sm, count_tests, d.stream));
         CU(ctx, cudaEventRecord(d.ev_b, d.stream));
         d.last_launches = 1;
-    } else if (engine == 2) {
-        const long long real_items = (long long)A.W * A.H * A.n_chunks;
-        long long want = knob("TRT_TUNE_SLOTS", 1 << 20);
-        if (want > real_items) want = real_items;
-        const int n_slots = (int)(((want + 255) / 256) * 256);
-        const size_t bytes = trt_wavefront_bytes(n_slots);
-        if (d.wf_bytes < bytes) {
-            if (d.wf_buf) cudaFree(d.wf_buf);
-            d.wf_buf = nullptr; d.wf_bytes = 0;
-            CU(ctx, cudaMalloc(&d.wf_buf, bytes));
-            d.wf_bytes = bytes;
-        }
-        WfState S{};
-        trt_wavefront_carve(d.wf_buf, n_slots, S);
-        CU(ctx, cudaEventRecord(d.ev_a, d.stream));
-        CU(ctx, trt_launch_wavefront(A, S, d.n_sms, (int*)&d.h_ctrs[15], &d.last_launches, d.stream));
-        CU(ctx, cudaEventRecord(d.ev_b, d.stream));
     } else {
         CU(ctx, cudaEventRecord(d.ev_a, d.stream));
         CU(ctx, trt_launch_pathtrace(A, d.n_sms, blocks_per_sm, brute, count_tests, d.stream));
@@ -366,8 +413,13 @@ double now_ms()
 
 }  // namespace
 
+// error plumbing for the other translation units of the library (nccl_glue.cu)
+int trt_set_error(trt_ctx* ctx, int code, const char* text) { return fail(ctx, code, "%s", text ? text : ""); }
+
 // ================================================================================================
 extern "C" {
+
+TRT_API int trt_device_of(const trt_ctx* ctx, int k) { return (ctx && k >= 0 && k < (int)ctx->devs.size()) ? ctx->devs[k].dev : -1; }
 
 TRT_API int trt_version(void) { return 100; }
 
@@ -433,6 +485,10 @@ TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
         e = cudaDeviceEnablePeerAccess(ctx->devs[k].dev, 0);
         if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { fail(nullptr, TRT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); trt_destroy(ctx); return TRT_ERR_CUDA; }
         cudaGetLastError();
+        // and the other way, so that the scene built on the root goes to the peers over NVLink (cudaMemcpyPeerAsync, trt_scene_set)
+        cudaSetDevice(ctx->devs[k].dev);
+        cudaDeviceEnablePeerAccess(ctx->devs[0].dev, 0);
+        cudaGetLastError();
     }
     *out = ctx;
     return TRT_OK;
@@ -441,13 +497,20 @@ TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
 TRT_API void trt_destroy(trt_ctx* ctx)
 {
     if (!ctx) return;
+    if (!ctx->devs.empty()) {
+        cudaSetDevice(ctx->devs[0].dev);
+        UploadRing& r = ctx->ring;
+        if (r.stream) { cudaStreamSynchronize(r.stream); cudaStreamDestroy(r.stream); }
+        for (cudaEvent_t ev : r.ev) if (ev) cudaEventDestroy(ev);
+        if (r.done) cudaEventDestroy(r.done);
+        if (r.h) cudaFreeHost(r.h);
+    }
     for (auto& d : ctx->devs) {
         cudaSetDevice(d.dev);
         if (d.stream) cudaStreamSynchronize(d.stream);
         free_scene(d);
         d.sky.release();
         if (d.accum) cudaFree(d.accum);
-        if (d.wf_buf) cudaFree(d.wf_buf);
         if (d.out) cudaFree(d.out);
         if (d.h_stage) cudaFreeHost(d.h_stage);
         for (cudaEvent_t ev : d.chunk_ev) cudaEventDestroy(ev);
@@ -496,57 +559,116 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
     const size_t n_texels = (size_t)nbMaterials * (size_t)tex_width * (size_t)tex_height;
     ctx->has_scene = false;
     const double t0 = now_ms();
-    for (auto& d : ctx->devs) {
+    const size_t ns = (size_t)(nbSpheres > 0 ? nbSpheres : 1), nt = (size_t)(nbTriangles > 0 ? nbTriangles : 1);
+    const size_t tex_bytes = sizeof(float4) * 3 * (n_texels > 0 ? n_texels : 1);
+    for (auto& d : ctx->devs) {            // the previous frame is over before its scene is overwritten
         CU(ctx, cudaSetDevice(d.dev));
         CU(ctx, cudaStreamSynchronize(d.stream));
-        const size_t ns = (size_t)(nbSpheres > 0 ? nbSpheres : 1), nt = (size_t)(nbTriangles > 0 ? nbTriangles : 1);
-        CU(ctx, d.sph_raw.ensure(sizeof(trt_sphere) * ns));
-        CU(ctx, d.sph.ensure(sizeof(float4) * ns));
-        CU(ctx, d.sph_mat.ensure(sizeof(float4) * 3 * ns));
-        CU(ctx, d.tri_raw.ensure(sizeof(trt_triangle) * nt));
-        CU(ctx, d.quel_mat.ensure(sizeof(int) * nt));
-        CU(ctx, d.tri.ensure(sizeof(float4) * 4 * nt + 256));
-        CU(ctx, d.tri_uv.ensure(sizeof(float4) * 2 * nt));
-        CU(ctx, d.tri_orig.ensure(sizeof(int) * nt));
-        CU(ctx, d.nodes.ensure(sizeof(float4) * 8 * nt));
-        CU(ctx, d.texels.ensure(sizeof(float4) * 3 * (n_texels > 0 ? n_texels : 1)));
-        CU(ctx, d.scratch.ensure(trt_build_scratch_bytes(nbTriangles)));
-        if (nbSpheres) CU(ctx, cudaMemcpyAsync(d.sph_raw.p, sphere_list, sizeof(trt_sphere) * nbSpheres, cudaMemcpyHostToDevice, d.stream));
-        if (nbTriangles) {
-            CU(ctx, d.mats_raw.ensure(sizeof(trt_material) * n_texels));
-            CU(ctx, d.ov_raw.ensure(sizeof(trt_mat_override) * (size_t)(n_overrides > 0 ? n_overrides : 1)));
+    }
+
+    // ---- root device: upload the caller's arrays, convert, build the BVH ----------------------------------
+    DeviceCtx& d = ctx->devs[0];
+    CU(ctx, cudaSetDevice(d.dev));
+    CU(ctx, d.sph_raw.ensure(sizeof(trt_sphere) * ns));
+    CU(ctx, d.sph.ensure(sizeof(float4) * ns));
+    CU(ctx, d.sph_mat.ensure(sizeof(float4) * 3 * ns));
+    CU(ctx, d.tri_raw.ensure(sizeof(trt_triangle) * nt));
+    CU(ctx, d.quel_mat.ensure(sizeof(int) * nt));
+    CU(ctx, d.tri.ensure(sizeof(float4) * 4 * nt + 256));
+    CU(ctx, d.tri_uv.ensure(sizeof(float4) * 2 * nt));
+    CU(ctx, d.tri_orig.ensure(sizeof(int) * nt));
+    CU(ctx, d.nodes.ensure(sizeof(float4) * 8 * nt));
+    CU(ctx, d.texels.ensure(tex_bytes));
+    CU(ctx, d.scratch.ensure(trt_build_scratch_bytes(nbTriangles)));
+    if (nbSpheres) CU(ctx, cudaMemcpyAsync(d.sph_raw.p, sphere_list, sizeof(trt_sphere) * nbSpheres, cudaMemcpyHostToDevice, d.stream));
+    if (nbTriangles) {
+        // texel slab: 80 B of FP64 per texel in the caller's array (hitinfo.h:6-13), packed to 10 floats on the way: half the
+        // bytes over PCIe, and out of pinned memory (C4, 1024^2 texels: 84 MB pageable took 8 ms)
+        CU(ctx, d.mats_raw.ensure(sizeof(float) * 10 * n_texels));
+        CU(ctx, d.ov_raw.ensure(sizeof(trt_mat_override) * (size_t)(n_overrides > 0 ? n_overrides : 1)));
+        auto pack_texels = [](char* dst, const char* src, size_t count) {
+            const double* in = (const double*)src; float* out = (float*)dst;
+            for (size_t k = 0; k < 10 * count; k++) out[k] = (float)in[k];
+        };
+        auto pack_copy_tri = [](char* dst, const char* src, size_t count) { memcpy(dst, src, count * sizeof(trt_triangle)); };
+        const bool staged = getenv("TRT_TUNE_STAGED_UP") == nullptr || atoi(getenv("TRT_TUNE_STAGED_UP")) != 0;
+        int rc;
+        if (staged && sizeof(trt_triangle) * (size_t)nbTriangles >= STAGED_MIN_BYTES) {
+            if ((rc = staged_upload(ctx, (char*)d.tri_raw.p, (const char*)triangle_list, (size_t)nbTriangles, sizeof(trt_triangle), sizeof(trt_triangle), pack_copy_tri)) != TRT_OK) return rc;
+        } else {
             CU(ctx, cudaMemcpyAsync(d.tri_raw.p, triangle_list, sizeof(trt_triangle) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
-            CU(ctx, cudaMemcpyAsync(d.quel_mat.p, quelMatPourTri, sizeof(int) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
-            CU(ctx, cudaMemcpyAsync(d.mats_raw.p, mat_list, sizeof(trt_material) * n_texels, cudaMemcpyHostToDevice, d.stream));
-            if (n_overrides > 0) CU(ctx, cudaMemcpyAsync(d.ov_raw.p, overrides, sizeof(trt_mat_override) * n_overrides, cudaMemcpyHostToDevice, d.stream));
         }
-        BuildInputs in{};
-        in.spheres_raw = (const double*)d.sph_raw.p; in.n_spheres = nbSpheres;
-        in.tris_raw = (const double*)d.tri_raw.p; in.n_tris = nbTriangles;
-        in.mats_raw = (const double*)d.mats_raw.p; in.tex_w = tex_width; in.tex_h = tex_height; in.n_materials = nbMaterials;
-        in.quel_mat = (const int*)d.quel_mat.p; in.overrides_raw = (const double*)d.ov_raw.p; in.n_overrides = nbTriangles ? n_overrides : 0;
-        in.scratch = d.scratch.p; in.scratch_bytes = d.scratch.cap;
-        BuildOutputs bo{};
-        bo.sph = (float4*)d.sph.p; bo.sph_mat = (float4*)d.sph_mat.p; bo.tri = (float4*)d.tri.p; bo.tri_uv = (float4*)d.tri_uv.p;
-        bo.tri_orig = (int*)d.tri_orig.p; bo.nodes = (float4*)d.nodes.p; bo.texels = (float4*)d.texels.p;
-        CU(ctx, trt_build_scene(in, bo, d.stream));
-        CU(ctx, cudaStreamSynchronize(d.stream));
-        if (d.mats_raw.cap > ((size_t)256 << 20)) d.mats_raw.release();      // big FP64 texture slabs are not kept around
+        CU(ctx, cudaMemcpyAsync(d.quel_mat.p, quelMatPourTri, sizeof(int) * nbTriangles, cudaMemcpyHostToDevice, d.stream));
+        if (staged && sizeof(trt_material) * n_texels >= STAGED_MIN_BYTES) {
+            if ((rc = staged_upload(ctx, (char*)d.mats_raw.p, (const char*)mat_list, n_texels, sizeof(trt_material), sizeof(float) * 10, pack_texels)) != TRT_OK) return rc;
+        } else {
+            std::vector<float> packed(10 * n_texels);
+            pack_texels((char*)packed.data(), (const char*)mat_list, n_texels);
+            CU(ctx, cudaMemcpyAsync(d.mats_raw.p, packed.data(), sizeof(float) * 10 * n_texels, cudaMemcpyHostToDevice, d.stream));
+            CU(ctx, cudaStreamSynchronize(d.stream));            // `packed` goes out of scope
+        }
+        if (n_overrides > 0) CU(ctx, cudaMemcpyAsync(d.ov_raw.p, overrides, sizeof(trt_mat_override) * n_overrides, cudaMemcpyHostToDevice, d.stream));
+    }
+    BuildInputs in{};
+    in.spheres_raw = (const double*)d.sph_raw.p; in.n_spheres = nbSpheres;
+    in.tris_raw = (const double*)d.tri_raw.p; in.n_tris = nbTriangles;
+    in.mats_packed = (const float*)d.mats_raw.p; in.tex_w = tex_width; in.tex_h = tex_height; in.n_materials = nbMaterials;
+    in.quel_mat = (const int*)d.quel_mat.p; in.overrides_raw = (const double*)d.ov_raw.p; in.n_overrides = nbTriangles ? n_overrides : 0;
+    in.scratch = d.scratch.p; in.scratch_bytes = d.scratch.cap;
+    BuildOutputs bo{};
+    bo.sph = (float4*)d.sph.p; bo.sph_mat = (float4*)d.sph_mat.p; bo.tri = (float4*)d.tri.p; bo.tri_uv = (float4*)d.tri_uv.p;
+    bo.tri_orig = (int*)d.tri_orig.p; bo.nodes = (float4*)d.nodes.p; bo.texels = (float4*)d.texels.p;
+    CU(ctx, trt_build_scene(in, bo, d.stream));
+    CU(ctx, cudaEventRecord(d.ev_c, d.stream));
+    if (3 * bo.max_depth + 2 > TRT_STACK_DEPTH)
+        return fail(ctx, TRT_ERR_INVALID, "BVH depth %d needs a traversal stack of %d entries (limit %d)", bo.max_depth, 3 * bo.max_depth + 2, TRT_STACK_DEPTH);
+    if (d.mats_raw.cap > ((size_t)256 << 20)) { CU(ctx, cudaStreamSynchronize(d.stream)); d.mats_raw.release(); }      // big texture slabs are not kept around
+    {
         DevScene& s = d.scene;
+        const float4* sky = s.sky; const int sky_w = s.sky_w, sky_h = s.sky_h;             // trt_sky_set is independent of the scene
+        s = DevScene{};
+        s.sky = sky; s.sky_w = sky_w; s.sky_h = sky_h;
         s.n_spheres = nbSpheres; s.sph = bo.sph; s.sph_mat = bo.sph_mat; s.sph64 = (const double*)d.sph_raw.p;
         s.n_tris = nbTriangles; s.tri = bo.tri; s.tri_uv = bo.tri_uv; s.tri_orig = bo.tri_orig; s.tri64 = (const double*)d.tri_raw.p;
         s.quel_mat = (const int*)d.quel_mat.p; s.nodes = bo.nodes; s.root = bo.root;
         s.texels = bo.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
         s.tri_tmin = bo.tri_tmin;
         s.root_lo = bo.root_lo; s.root_hi = bo.root_hi;
-        if (3 * bo.max_depth + 2 > TRT_STACK_DEPTH)
-            return fail(ctx, TRT_ERR_INVALID, "BVH depth %d needs a traversal stack of %d entries (limit %d)", bo.max_depth, 3 * bo.max_depth + 2, TRT_STACK_DEPTH);
-        if (&d == &ctx->devs[0]) {
-            ctx->info.n_nodes = bo.n_wide_nodes;
-            ctx->info.n_leaves = nbTriangles;
-            ctx->info.max_depth = bo.max_depth; ctx->info.n_twins = bo.n_twins; ctx->info.sah_cost = bo.sah_cost;
-        }
     }
+    ctx->info.n_nodes = bo.n_wide_nodes;
+    ctx->info.n_leaves = nbTriangles;
+    ctx->info.max_depth = bo.max_depth; ctx->info.n_twins = bo.n_twins; ctx->info.sah_cost = bo.sah_cost;
+
+    // ---- the other devices of the ctx get the BUILT scene over NVLink: one build, N - 1 peer copies in parallel ----------
+    const size_t n_nodes = (size_t)(bo.n_wide_nodes > 0 ? bo.n_wide_nodes : 1);
+    for (size_t k = 1; k < ctx->devs.size(); k++) {
+        DeviceCtx& q = ctx->devs[k];
+        CU(ctx, cudaSetDevice(q.dev));
+        CU(ctx, q.sph.ensure(sizeof(float4) * ns));
+        CU(ctx, q.sph_mat.ensure(sizeof(float4) * 3 * ns));
+        CU(ctx, q.tri.ensure(sizeof(float4) * 4 * nt + 256));
+        CU(ctx, q.tri_uv.ensure(sizeof(float4) * 2 * nt));
+        CU(ctx, q.tri_orig.ensure(sizeof(int) * nt));
+        CU(ctx, q.nodes.ensure(sizeof(float4) * 8 * n_nodes));
+        CU(ctx, q.texels.ensure(tex_bytes));
+        CU(ctx, cudaStreamWaitEvent(q.stream, d.ev_c, 0));
+        struct { Buf* dst; Buf* src; size_t bytes; } copies[] = {
+            {&q.sph, &d.sph, sizeof(float4) * (size_t)nbSpheres}, {&q.sph_mat, &d.sph_mat, sizeof(float4) * 3 * (size_t)nbSpheres},
+            {&q.tri, &d.tri, sizeof(float4) * 4 * (size_t)nbTriangles}, {&q.tri_uv, &d.tri_uv, sizeof(float4) * 2 * (size_t)nbTriangles},
+            {&q.tri_orig, &d.tri_orig, sizeof(int) * (size_t)nbTriangles}, {&q.nodes, &d.nodes, nbTriangles ? sizeof(float4) * 8 * n_nodes : 0},
+            {&q.texels, &d.texels, sizeof(float4) * 3 * n_texels},
+        };
+        for (auto& c : copies)
+            if (c.bytes) CU(ctx, cudaMemcpyPeerAsync(c.dst->p, q.dev, c.src->p, d.dev, c.bytes, q.stream));
+        DevScene& s = q.scene;
+        const float4* sky = s.sky; const int sky_w = s.sky_w, sky_h = s.sky_h;
+        s = d.scene;
+        s.sky = sky; s.sky_w = sky_w; s.sky_h = sky_h;
+        s.sph = (const float4*)q.sph.p; s.sph_mat = (const float4*)q.sph_mat.p; s.tri = (const float4*)q.tri.p; s.tri_uv = (const float4*)q.tri_uv.p;
+        s.tri_orig = (const int*)q.tri_orig.p; s.nodes = (const float4*)q.nodes.p; s.texels = (const float4*)q.texels.p;
+        s.sph64 = nullptr; s.tri64 = nullptr; s.quel_mat = nullptr;       // the FP64 primary pass (trt_primary) runs on the root only
+    }
+    for (auto& q : ctx->devs) { CU(ctx, cudaSetDevice(q.dev)); CU(ctx, cudaStreamSynchronize(q.stream)); }
     ctx->info.ms_build = now_ms() - t0;
     ctx->has_scene = true;
     return TRT_OK;
@@ -660,6 +782,21 @@ TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d
     return copy_out(ctx, d, npix, canva, albedo_tab, normal_tab);
 }
 
+TRT_API int trt_resolve_hdr_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                                   float* d_radiance, float* d_albedo, float* d_normal)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    if (!d_accum || !d_radiance || !d_albedo || !d_normal) return fail(ctx, TRT_ERR_INVALID, "NULL device buffer");
+    DeviceCtx& d = ctx->devs[0];
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    CU(ctx, cudaSetDevice(d.dev));
+    const int divisor = params->sample_total > 0 ? params->sample_total : params->nbRayonParPixel;
+    CU(ctx, trt_launch_resolve_hdr((int)npix, divisor, (const long long*)d_accum, d_radiance, d_albedo, d_normal, d.n_sms, d.stream));
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    return TRT_OK;
+}
+
 TRT_API int trt_resolve_hdr(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
                             float* radiance, float* albedo, float* normal)
 {
@@ -671,8 +808,7 @@ TRT_API int trt_resolve_hdr(trt_ctx* ctx, const trt_params* params, const int64_
     CU(ctx, cudaSetDevice(d.dev));
     if ((rc = ensure_out(ctx, d, npix)) != TRT_OK) return rc;
     float* buf = (float*)d.out;                    // 9*npix doubles are room for 9*npix floats
-    const int divisor = params->sample_total > 0 ? params->sample_total : params->nbRayonParPixel;
-    CU(ctx, trt_launch_resolve_hdr((int)npix, divisor, (const long long*)d_accum, buf, buf + 3 * npix, buf + 6 * npix, d.n_sms, d.stream));
+    if ((rc = trt_resolve_hdr_device(ctx, params, d_accum, buf, buf + 3 * npix, buf + 6 * npix)) != TRT_OK) return rc;
     CU(ctx, cudaMemcpyAsync(radiance, buf, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaMemcpyAsync(albedo, buf + 3 * npix, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
     CU(ctx, cudaMemcpyAsync(normal, buf + 6 * npix, sizeof(float) * 3 * npix, cudaMemcpyDeviceToHost, d.stream));
@@ -743,6 +879,67 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
     return TRT_OK;
 }
 
+// One process per GPU (nccl_glue.cu): this rank's share of the samples (or tiles), NCCL reduce onto rank 0, rank 0 resolves.
+TRT_API int trt_render_distributed(trt_ctx* ctx, const trt_params* params, void* nccl_comm, int rank, int n_ranks,
+                                   trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    if (ctx->devs.size() != 1) return fail(ctx, TRT_ERR_INVALID, "trt_render_distributed works on a single-device ctx (one process per GPU)");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(ctx, TRT_ERR_INVALID, "rank %d of %d", rank, n_ranks);
+    if (n_ranks > 1 && !nccl_comm) return fail(ctx, TRT_ERR_INVALID, "nccl_comm is NULL");
+    if (params->tile_part != 0) return fail(ctx, TRT_ERR_INVALID, "tile_part is chosen by trt_render_distributed (TRT_FLAG_TILE_SPLIT)");
+    const double t0 = now_ms();
+    DeviceCtx& d = ctx->devs[0];
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    const int spp = params->nbRayonParPixel;
+    CU(ctx, cudaSetDevice(d.dev));
+    if ((rc = ensure_accum(ctx, d, npix)) != TRT_OK) return rc;
+    CU(ctx, cudaMemsetAsync(d.accum, 0, sizeof(long long) * 9 * npix, d.stream));
+    const bool tile_split = n_ranks > 1 && (params->flags & TRT_FLAG_TILE_SPLIT) != 0;
+    int s0 = (int)((long long)spp * rank / n_ranks), s1 = (int)((long long)spp * (rank + 1) / n_ranks), t_off = 0, t_stride = 1;
+    if (tile_split) { s0 = 0; s1 = spp; t_off = rank; t_stride = n_ranks; }
+    if (s1 > s0) {
+        if ((rc = launch_trace(ctx, d, params, s1 - s0, params->sample_offset + s0, d.accum, t_off, t_stride)) != TRT_OK) return rc;
+    } else {
+        CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+        CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+        memset(d.h_ctrs, 0, sizeof(unsigned long long) * 16);
+        d.last_launches = 0;
+    }
+    CU(ctx, cudaEventRecord(d.ev_c, d.stream));
+    if (rank == 0 && canva && albedo_tab && normal_tab) ensure_stage(d, sizeof(double) * 9 * npix);      // while the GPU traces
+    if (n_ranks > 1 && (rc = trt_reduce_nccl(ctx, nccl_comm, (int64_t*)d.accum, 9 * npix, 0)) != TRT_OK) return rc;
+    int launches = d.last_launches;
+    if (rank == 0) {
+        if ((rc = ensure_out(ctx, d, npix)) != TRT_OK) return rc;
+        trt_params rp = *params;
+        if (rp.sample_total <= 0) rp.sample_total = spp;
+        const long long* src = d.accum;
+        if ((rc = resolve_common(ctx, &rp, &src, 1, d.out, d.out + 3 * npix, d.out + 6 * npix)) != TRT_OK) return rc;
+        launches++;
+        CU(ctx, cudaEventRecord(d.ev_d, d.stream));
+        if ((rc = copy_out(ctx, d, npix, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;
+    } else {
+        CU(ctx, cudaEventRecord(d.ev_d, d.stream));
+    }
+    CU(ctx, cudaStreamSynchronize(d.stream));
+    if ((rc = check_watchdog(ctx)) != TRT_OK) return rc;
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        trt_params mine = *params;
+        mine.nbRayonParPixel = s1 - s0;
+        collect_stats(ctx, &mine, stats, true);                          // this rank's paths and rays
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, d.ev_c, d.ev_d) == cudaSuccess) stats->ms_reduce_resolve = ms;
+        stats->kernel_launches = launches;
+        stats->ms_total = now_ms() - t0;
+        stats->ms_d2h = stats->ms_total - stats->ms_trace - stats->ms_reduce_resolve;
+        if (stats->ms_d2h < 0) stats->ms_d2h = 0;
+    }
+    return TRT_OK;
+}
+
 TRT_API int trt_primary(trt_ctx* ctx, const trt_params* params, double* t, int* id, trt_vec3* normal, trt_vec3* albedo)
 {
     int rc = check_params(ctx, params);
@@ -765,6 +962,27 @@ TRT_API int trt_primary(trt_ctx* ctx, const trt_params* params, double* t, int* 
     if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, P.id, sizeof(int) * npix, cudaMemcpyDeviceToHost, d.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
     cudaFree(buf);
+    CU(ctx, e);
+    return TRT_OK;
+}
+
+TRT_API int trt_primary_fp32(trt_ctx* ctx, const trt_params* params, float* t, int* id)
+{
+    int rc = check_params(ctx, params);
+    if (rc != TRT_OK) return rc;
+    DeviceCtx& d = ctx->devs[0];
+    const size_t npix = (size_t)params->largeur_image * params->hauteur_image;
+    CU(ctx, cudaSetDevice(d.dev));
+    RenderArgs A{};
+    fill_camera_args(A, d, params);
+    int* d_id = nullptr;
+    CU(ctx, cudaMalloc(&d_id, (sizeof(int) + sizeof(float)) * npix));
+    float* d_t = (float*)(d_id + npix);
+    cudaError_t e = trt_launch_primary_fp32(A, d_id, d_t, d.stream);
+    if (e == cudaSuccess && id) e = cudaMemcpyAsync(id, d_id, sizeof(int) * npix, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, d_t, sizeof(float) * npix, cudaMemcpyDeviceToHost, d.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d.stream);
+    cudaFree(d_id);
     CU(ctx, e);
     return TRT_OK;
 }

@@ -9,7 +9,7 @@
 //   2. morton_keys     36-bit Morton code of the centroid << 28 | triangle index  (unique 64-bit keys)
 //   3. radix sort      cub::DeviceRadixSort (library; the build is not on the per-ray path)
 //   4. emit_leaves     triangles re-laid out in sorted (leaf) order: A, AB, AC, N + ids as 4 float4 (64 B)
-//   4b. group_heads    triangles with IDENTICAL boxes (the two halves of a quad, the back faces of a double-faced mesh, crossed
+//   4b. group_marks/heads  triangles with IDENTICAL boxes (the two halves of a quad, the back faces of a double-faced mesh, crossed
 //                      plant quads: 2, 4 or 8 triangles per box in the reference's Minecraft exports) are neighbours after
 //                      the sort and become ONE leaf: the hierarchy is built over the distinct boxes, and a leaf step tests
 //                      the whole run (count in the head record).  Without this the tree has to separate equal boxes with
@@ -53,26 +53,26 @@ __global__ void convert_spheres(const double* __restrict__ raw, int n, float4* s
     mat[3 * k + 2] = make_float4((float)s[11], (float)s[13], 0.0f, 0.0f);
 }
 
-// material[] slab -> texel records, with the per-ordinal overrides of texture.h:71-87 baked in.
-__global__ void convert_texels(const double* __restrict__ raw, size_t n_texels, int texels_per_mat,
+// material[] slab (packed to 10 floats per texel on the host) -> texel records, with the per-ordinal overrides of texture.h:71-87 baked in.
+__global__ void convert_texels(const float* __restrict__ raw, size_t n_texels, int texels_per_mat,
                                const MatOverrideDev* __restrict__ ov, int n_ov, float4* out)
 {
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < n_texels; t += (size_t)gridDim.x * blockDim.x) {
-        const double* m = raw + 10 * t;
-        double dr = m[0], dg = m[1], db = m[2], er = m[3], eg = m[4], eb = m[5], es = m[6], rs = m[7], al = m[8], ix = m[9];
+        const float* m = raw + 10 * t;
+        float dr = m[0], dg = m[1], db = m[2], er = m[3], eg = m[4], eb = m[5], es = m[6], rs = m[7], al = m[8], ix = m[9];
         const int ordinal = (int)(t / (size_t)texels_per_mat);
         for (int k = 0; k < n_ov; k++) {
             if (ov[k].ordinal != ordinal) continue;
             const unsigned mask = ov[k].mask;
-            if (mask & 1u) { er = ov[k].ec[0]; eg = ov[k].ec[1]; eb = ov[k].ec[2]; }
-            if (mask & 2u) es = ov[k].es;
-            if (mask & 4u) rs = ov[k].rs;
-            if (mask & 8u) al = ov[k].alpha;
-            if (mask & 16u) ix = ov[k].index;
+            if (mask & 1u) { er = (float)ov[k].ec[0]; eg = (float)ov[k].ec[1]; eb = (float)ov[k].ec[2]; }
+            if (mask & 2u) es = (float)ov[k].es;
+            if (mask & 4u) rs = (float)ov[k].rs;
+            if (mask & 8u) al = (float)ov[k].alpha;
+            if (mask & 16u) ix = (float)ov[k].index;
         }
-        out[3 * t + 0] = make_float4((float)dr, (float)dg, (float)db, (float)al);
-        out[3 * t + 1] = make_float4((float)er, (float)eg, (float)eb, (float)es);
-        out[3 * t + 2] = make_float4((float)rs, (float)ix, 0.0f, 0.0f);
+        out[3 * t + 0] = make_float4(dr, dg, db, al);
+        out[3 * t + 1] = make_float4(er, eg, eb, es);
+        out[3 * t + 2] = make_float4(rs, ix, 0.0f, 0.0f);
     }
 }
 
@@ -160,24 +160,27 @@ __global__ void emit_leaves(int n, const unsigned long long* __restrict__ keys, 
     leaf_hi[p] = make_float4(hi.x + pad, hi.y + pad, hi.z + pad, 0.0f);
 }
 
-// head[p] = 1 when the triangle at sorted position p starts a new box (group == 0: every triangle is its own leaf)
-__global__ void group_heads(int n, const unsigned long long* __restrict__ keys, const float4* __restrict__ box_lo,
-                            const float4* __restrict__ box_hi, int group, int cap, int* head)
+// Runs of equal boxes, cut every `cap` triangles.  run_mark[p] = p when the box at sorted position p differs from its
+// predecessor's (or p == 0, or grouping is off), else 0; an inclusive max-scan turns that into the start of p's run, and
+// head[p] = 1 where (p - start) is a multiple of cap: a run of 40 identical boxes becomes leaves of 16 + 16 + 8.
+__global__ void group_marks(int n, const unsigned long long* __restrict__ keys, const float4* __restrict__ box_lo,
+                            const float4* __restrict__ box_hi, int group, int* run_mark)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    int h = 1;
+    int differs = 1;
     if (p > 0 && group) {
-        // walk back to the start of the run of equal boxes (at most cap - 1 steps): a run is cut every `cap` triangles
-        int back = 0;
-        for (int q = p; q > 0 && back < cap; q--, back++) {
-            const int k = (int)(keys[q] & IDX_MASK), k2 = (int)(keys[q - 1] & IDX_MASK);
-            const float4 a = box_lo[k], b = box_hi[k], c = box_lo[k2], d = box_hi[k2];
-            if (!(a.x == c.x && a.y == c.y && a.z == c.z && b.x == d.x && b.y == d.y && b.z == d.z)) break;
-        }
-        h = (back == 0 || back >= cap) ? 1 : 0;      // back == 0: the box differs from the previous triangle's; back == cap: cut
+        const int k = (int)(keys[p] & IDX_MASK), k2 = (int)(keys[p - 1] & IDX_MASK);
+        const float4 a = box_lo[k], b = box_hi[k], c = box_lo[k2], d = box_hi[k2];
+        differs = !(a.x == c.x && a.y == c.y && a.z == c.z && b.x == d.x && b.y == d.y && b.z == d.z);
     }
-    head[p] = h;
+    run_mark[p] = differs ? p : 0;
+}
+
+__global__ void group_heads(int n, const int* __restrict__ run_start, int cap, int* head)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) head[p] = ((p - run_start[p]) % cap == 0) ? 1 : 0;
 }
 
 __global__ void group_first(int n, const int* __restrict__ head, const int* __restrict__ gpos, int* gfirst)
@@ -439,6 +442,8 @@ size_t trt_build_scratch_bytes(int n_tris)
     cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n_tris, 0, 64, 0);
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, n_tris, 0);
     if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
+    cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, cub::Max(), n_tris, 0);
+    if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
     const size_t n = (size_t)n_tris;
     return 8 * align256(sizeof(float4) * n) + 2 * align256(8 * n) + 3 * align256(sizeof(int2) * n) + 6 * align256(sizeof(int) * n) + 256 + align256(cub_bytes) + 4096;
 }
@@ -457,7 +462,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     const size_t n_texels = (size_t)in.n_materials * (size_t)in.tex_w * (size_t)in.tex_h;
     if (n_texels > 0) {
         int grid = (int)((n_texels + TB - 1) / TB); if (grid > 148 * 16) grid = 148 * 16;
-        convert_texels<<<grid, TB, 0, stream>>>(in.mats_raw, n_texels, in.tex_w * in.tex_h,
+        convert_texels<<<grid, TB, 0, stream>>>(in.mats_packed, n_texels, in.tex_w * in.tex_h,
                                                 (const MatOverrideDev*)in.overrides_raw, in.n_overrides, out.texels);
         BT(cudaGetLastError());
     }
@@ -469,6 +474,8 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     size_t cub_bytes = 0, scan_bytes = 0;
     BT(cub::DeviceRadixSort::SortKeys(nullptr, cub_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, n, 0, 64, stream));
     BT(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, n, stream));
+    if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
+    BT(cub::DeviceScan::InclusiveScan(nullptr, scan_bytes, (const int*)nullptr, (int*)nullptr, cub::Max(), n, stream));
     if (scan_bytes > cub_bytes) cub_bytes = scan_bytes;
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += align256(bytes); return o; };
@@ -515,7 +522,13 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
 
     const char* capv = getenv("TRT_TUNE_RUNCAP");
     const int run_cap = (capv && *capv && atoi(capv) > 0) ? atoi(capv) : 16;
-    group_heads<<<grid_n, TB, 0, stream>>>(n, keys_b, box_lo, box_hi, group, run_cap, ghead);
+    {
+        int* run_mark = parent_leaf;            // free until the LBVH hierarchy pass, which comes after the grouping
+        group_marks<<<grid_n, TB, 0, stream>>>(n, keys_b, box_lo, box_hi, group, run_mark);
+        size_t tmp = cub_bytes;
+        BT(cub::DeviceScan::InclusiveScan(base + o_cub, tmp, run_mark, gpos, cub::Max(), n, stream));      // gpos = start of the run, for now
+        group_heads<<<grid_n, TB, 0, stream>>>(n, gpos, run_cap, ghead);
+    }
     { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, ghead, gpos, n, stream)); }
     group_first<<<grid_n, TB, 0, stream>>>(n, ghead, gpos, gfirst);
     BT(cudaGetLastError());

@@ -298,6 +298,46 @@ cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, 
     return cudaGetLastError();
 }
 
+// ---- the path-tracing kernel's own first hit through PIXEL CENTRES -----------------------------------------------
+// Parity test 1 compares the FP64 pass of primary.cu with the CPU path; this kernel answers the other half of the
+// question: which primitive does the FP32 machinery K2 actually renders with (camera_ray without jitter, sphere_root,
+// the BVH walk, triangle_test, first-wins ties) find for the same pixel-centre rays?  Ids in the caller's numbering.
+template <bool HAS_TRIS>
+__global__ void __launch_bounds__(128)
+primary_fp32_kernel(const __grid_constant__ RenderArgs A, int* __restrict__ id_out, float* __restrict__ t_out)
+{
+    const DevScene& sc = A.scene;
+    const int pixel = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pixel >= A.W * A.H) return;
+    const int px = pixel % A.W, py = pixel / A.W;
+    const float u = (float)px * A.inv_wm1, v = (float)py * A.inv_hm1;                  // main.c:265-266 without the jitter
+    const float3 direction = fma3(A.cam_hor, u, fma3(A.cam_ver, v, A.cam_corner));
+    const float3 dest = fma3(direction, A.focus, A.cam_origin);
+    const float3 o = A.cam_origin;
+    const float3 d = normalize3(dest - o);
+    Trav tr;
+    int stack[TRT_STACK_DEPTH];
+    TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
+    ray_begin<HAS_TRIS, false, false>(sc, sc.sph, o, d, TRT_NO_PRIM, -1, false, tr, stack, cnt);
+    if (HAS_TRIS) {
+        const float3 idir = safe_inverse(d);
+        const float3 ood = f3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        while (tr.node != TRT_TRAV_DONE) bvh_step_unified<false>(sc, o, d, idir, ood, -1, -1, false, tr, stack, cnt);
+    }
+    int id = -1;
+    if (tr.prim != TRT_NO_PRIM) id = tr.prim < sc.n_spheres ? tr.prim : sc.n_spheres + __ldg(sc.tri_orig + (tr.prim - sc.n_spheres));
+    if (id_out) id_out[pixel] = id;
+    if (t_out) t_out[pixel] = tr.prim != TRT_NO_PRIM ? tr.t : 0.0f;
+}
+
+cudaError_t trt_launch_primary_fp32(const RenderArgs& A, int* id, float* t, cudaStream_t stream)
+{
+    const int n = A.W * A.H, grid = (n + 127) / 128;
+    if (A.scene.n_tris > 0) primary_fp32_kernel<true><<<grid, 128, 0, stream>>>(A, id, t);
+    else primary_fp32_kernel<false><<<grid, 128, 0, stream>>>(A, id, t);
+    return cudaGetLastError();
+}
+
 // ---- launchers -------------------------------------------------------------------------------------
 template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)

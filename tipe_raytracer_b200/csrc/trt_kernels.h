@@ -40,7 +40,7 @@ struct RenderArgs {
     int pp_refill_min;                  // lanes re-arm from the ray-ready ring once this many of the warp are idle
     int pp_exit_below;                  // ... or the warp shades what it has when fewer rays than this are in flight or waiting
     unsigned pp_per_tile, pp_m_per_tile, pp_m_spp; int pp_fit32;   // decode_path: 32 * spp and the reciprocals (fastdiv)
-    int count_tests, wf_blocks, wf_check; // wavefront engine: count box/tri tests; trace CTAs per SM; waves between liveness checks
+    int count_tests;
     long long n_items;
     unsigned long long* item_counter;   // zeroed before launch
     unsigned long long* counters;       // [0] rays [1] box tests [2] triangle tests [3] sphere tests
@@ -53,31 +53,11 @@ struct ResolveArgs {
     double *canva, *albedo, *normal;    // [W*H][3]
 };
 
-// Wavefront engine state: one SLOT per in-flight path, SoA in global memory (see wavefront.cu).
-struct WfState {
-    int n_slots;                 // multiple of 256
-    float4* ray_o;               // (origin, bits(src_prim))
-    float4* ray_d;               // (direction of the ray to trace next, bits(src_twin))
-    float4* hit;                 // (t, bits(prim), u, v)  written by the trace kernel
-    float4* path_T;              // (rayColor, cur_index)
-    float4* path_L;              // (incomingLight, bits(meta))   meta = phase | is_alpha<<2 | bounce<<3 | alpha_depth<<16
-    float4* aov_a;               // (albedo AOV, bits(pixel))
-    float4* aov_n;               // (normal AOV, bits(current sample))
-    float4* dnext;               // (bounce direction parked during an AO query, bits(end sample))
-    long long* acc;              // [9][n_slots] sums of the slot's current item
-    unsigned char* rflag;        // 0 no ray, 1 closest-hit query, 2 any-hit query
-    int* live;                   // slots that are not dead yet
-    unsigned long long* cursor;  // work counter of the trace kernel, reset by the shade kernel
-};
-size_t trt_wavefront_bytes(int n_slots);
-void trt_wavefront_carve(void* base, int n_slots, WfState& S);
-// Runs shade/trace waves until every slot is dead.  Returns the number of kernel launches in *launches.
-cudaError_t trt_launch_wavefront(const RenderArgs& A, WfState& S, int n_sms, int* h_live_pinned, int* launches, cudaStream_t stream);
-
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream);
 // slot-pool kernel for triangle meshes (pathtrace_pool.cu); blocks_per_sm 0 = default
 cudaError_t trt_launch_pathtrace_pool(const RenderArgs& A, int n_sms, int blocks_per_sm, bool count_tests, cudaStream_t stream);
 size_t trt_pool_smem_bytes(const RenderArgs& A);
+cudaError_t trt_launch_primary_fp32(const RenderArgs& A, int* id, float* t, cudaStream_t stream);     // K2's FP32 first hit, pixel centres
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
 cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, float* radiance, float* albedo, float* normal, int n_sms, cudaStream_t stream);
 
@@ -95,7 +75,7 @@ cudaError_t trt_launch_primary(const PrimaryArgs& P, cudaStream_t stream);
 struct BuildInputs {
     const double* spheres_raw;   int n_spheres;     // 14 doubles each
     const double* tris_raw;      int n_tris;        // 25 doubles each
-    const double* mats_raw;      int tex_w, tex_h, n_materials;   // 10 doubles per texel
+    const float*  mats_packed;   int tex_w, tex_h, n_materials;   // 10 floats per texel: the caller's material structs, rounded to FP32 on the host
     const int*    quel_mat;                         // [n_tris]
     const double* overrides_raw; int n_overrides;   // trt_mat_override, 8 doubles each (first = ordinal|mask)
     void* scratch; size_t scratch_bytes;            // device scratch of at least trt_build_scratch_bytes(n_tris)

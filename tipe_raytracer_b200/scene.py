@@ -342,4 +342,7 @@ CONFIGS = {
     "C5": readme_benchmark,
     "C3b": pyramide_eau,
     "C4sky": tree_mesh_sky,
+    # BASELINE.md §4 "large triangle mesh": the tree instanced 24 x 24 times = 1 032 192 triangles (SYNTHETIC; the shipped
+    # 1st_mc_world holds one 1 792-triangle tree), C4's resolution / bounces, camera pulled back to see the whole forest
+    "C4big": lambda: tree_mesh(grid=24),
 }
