@@ -128,6 +128,8 @@ typedef struct trt_stats {
     double   ms_total;         /* whole call, host clock */
     int      kernel_launches;  /* kernels of this library launched by the call */
     int      reserved;
+    uint64_t rays_skipped;     /* of `rays`: ambient-occlusion rays of a path's LAST bounce, which main.c:220 traces although their
+                                  result (a factor on rayColor) is never read; counted for parity with the reference, not traced */
 } trt_stats;
 
 typedef struct trt_ctx trt_ctx;

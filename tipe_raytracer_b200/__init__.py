@@ -69,6 +69,7 @@ class TrtStats(C.Structure):
         ("box_tests", C.c_uint64), ("tri_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
         ("ms_trace", C.c_double), ("ms_reduce_resolve", C.c_double), ("ms_d2h", C.c_double), ("ms_total", C.c_double),
         ("kernel_launches", C.c_int), ("reserved", C.c_int),
+        ("rays_skipped", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -312,6 +312,9 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
     A.hk_min = knob("TRT_TUNE_HK_MIN", 28);          // another housekeeping pass while fewer than 28/32 of the live lanes have BVH work (and some lane has a hit to consume)
     A.defer = knob("TRT_TUNE_DEFER", 3);
     A.exp_flags = knob("TRT_TUNE_EXP", 0);
+    A.top_nodes = knob("TRT_TUNE_TOPK", 0);
+    if (A.top_nodes > ctx->info.n_nodes) A.top_nodes = ctx->info.n_nodes;
+    if (A.top_nodes > 256) A.top_nodes = 256;
     A.item_order = knob("TRT_TUNE_ORDER", d.scene.n_tris > 0 ? 1 : 0);   // meshes: a warp starts on the samples of 2-3 neighbouring pixels (coherent primary rays, +2-3 %); spheres: one tile (+5 %)
     A.count_tests = count_tests ? 1 : 0;
     const int blocks_per_sm = knob("TRT_TUNE_BLOCKS", 0);     // 0: kernel default (4 CTAs of 256 threads per SM, 64 registers)
@@ -385,13 +388,14 @@ void collect_stats(trt_ctx* ctx, const trt_params* p, trt_stats* st, bool traced
 {
     if (!st) return;
     if (traced) {
-        st->rays = st->box_tests = st->tri_tests = st->sphere_tests = 0;
+        st->rays = st->box_tests = st->tri_tests = st->sphere_tests = st->rays_skipped = 0;
         st->ms_trace = 0.0;
         for (auto& d : ctx->devs) {
             float ms = 0.0f;
             cudaSetDevice(d.dev);
             if (cudaEventElapsedTime(&ms, d.ev_a, d.ev_b) == cudaSuccess && ms > st->ms_trace) st->ms_trace = ms;
             st->rays += d.h_ctrs[1]; st->box_tests += d.h_ctrs[2]; st->tri_tests += d.h_ctrs[3]; st->sphere_tests += d.h_ctrs[4];
+            st->rays_skipped += d.h_ctrs[12];
         }
         st->paths = (uint64_t)p->largeur_image * (uint64_t)p->hauteur_image * (uint64_t)p->nbRayonParPixel;
     }

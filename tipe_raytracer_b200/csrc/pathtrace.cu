@@ -32,7 +32,7 @@
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER, bool TOP = false>
 __global__ void __launch_bounds__(PT_THREADS, HAS_TRIS ? PT_MIN_BLOCKS_MESH : PT_MIN_BLOCKS)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
@@ -40,6 +40,25 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     float4* s_sph = smem;                                   // [n_spheres]
     float4* s_mat = smem + A.scene.n_spheres;               // [3*n_spheres]
     long long* s_acc = (long long*)(smem + 4 * A.scene.n_spheres);   // [9][PT_THREADS] per-lane sums of the current item
+    // TOP: the first A.top_nodes wide nodes of the BVH (its top levels) staged into shared memory with one TMA bulk copy
+    // (cp.async.bulk global -> shared, completion on an mbarrier): north_star's "top levels staged through shared memory or TMA"
+    float4* s_top = (float4*)(s_acc + 9 * PT_THREADS);
+    if (TOP) {
+        unsigned long long* bar = (unsigned long long*)(s_top + 8 * A.top_nodes);
+        const unsigned bar_s = (unsigned)__cvta_generic_to_shared(bar), dst_s = (unsigned)__cvta_generic_to_shared(s_top);
+        const unsigned bytes = (unsigned)A.top_nodes * 128u;
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar_s));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar_s), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"(dst_s), "l"(A.scene.nodes), "r"(bytes), "r"(bar_s) : "memory");
+        }
+        __syncthreads();
+        unsigned done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar_s) : "memory");
+    }
     for (int k = threadIdx.x; k < A.scene.n_spheres; k += blockDim.x) s_sph[k] = A.scene.sph[k];
     for (int k = threadIdx.x; k < 3 * A.scene.n_spheres; k += blockDim.x) s_mat[k] = A.scene.sph_mat[k];
 #pragma unroll
@@ -67,7 +86,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     int stack[TRT_STACK_DEPTH];
     int pend = 0;                           // DEFER: the parked leaf (0 = none), see bvh_trip_deferred
 
-    unsigned ray_count = 0;
+    unsigned ray_count = 0, skipped = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
     // schedule counters (COUNT builds only, warp-uniform): BVH-loop trips, lanes inside / at a node / at a leaf per trip,
     // loop sessions, housekeeping passes, lanes consuming a hit per pass
@@ -92,6 +111,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 my_acc[0 * PT_THREADS] += to_fixed(res.L.x, A.sample_clamp);      my_acc[1 * PT_THREADS] += to_fixed(res.L.y, A.sample_clamp);      my_acc[2 * PT_THREADS] += to_fixed(res.L.z, A.sample_clamp);
                 my_acc[3 * PT_THREADS] += to_fixed(res.albedo.x, A.sample_clamp); my_acc[4 * PT_THREADS] += to_fixed(res.albedo.y, A.sample_clamp); my_acc[5 * PT_THREADS] += to_fixed(res.albedo.z, A.sample_clamp);
                 my_acc[6 * PT_THREADS] += to_fixed(res.normal.x, A.sample_clamp); my_acc[7 * PT_THREADS] += to_fixed(res.normal.y, A.sample_clamp); my_acc[8 * PT_THREADS] += to_fixed(res.normal.z, A.sample_clamp);
+                ray_count += res.dead_ao; skipped += res.dead_ao;
                 s_cur++;
                 phase = PH_NEW;
             } else {
@@ -216,7 +236,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
                 // if-if: every trip, each lane does whatever it is at — a node visit or a leaf test (measured faster than
                 // deferring, voting on or pairing the two on B200, profiles/README.md)
-                if (DEFER) bvh_trip_deferred<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, A.defer, tr, pend, stack, cnt);
+                if (DEFER) bvh_trip_deferred<COUNT, TOP>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, A.defer, tr, pend, stack, cnt, 0, s_top, A.top_nodes);
                 else if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
             }
         }
@@ -227,6 +247,12 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
     if (lane == 0 && rc) atomicAdd(A.counters + 0, rc);
+    if (A.use_ao) {
+        unsigned long long sk = skipped;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sk += __shfl_xor_sync(0xffffffffu, sk, off);
+        if (lane == 0 && sk) atomicAdd(A.counters + 11, sk);
+    }
     if (COUNT) {
         unsigned long long b = cnt.box_tests, t = cnt.tri_tests, s = cnt.sphere_tests;
 #pragma unroll
@@ -339,7 +365,7 @@ cudaError_t trt_launch_primary_fp32(const RenderArgs& A, int* id, float* t, cuda
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false, bool TOP = false>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
 {
     {
@@ -350,26 +376,28 @@ static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cu
         const char* v = getenv("TRT_TUNE_CARVEOUT");
         if (v && *v) pct = atoi(v);
         if (pct > 100) pct = 100;
-        cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         // more than ~460 spheres: the sphere table + the per-lane sums pass the 48 KB a kernel gets without asking
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
     }
-    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER><<<grid, PT_THREADS, smem, stream>>>(A);
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream)
 {
-    const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4) + sizeof(long long) * 9 * PT_THREADS;
+    const bool top = A.top_nodes > 0 && A.scene.n_tris > 0 && !brute && A.defer > 0 && !count_tests;
+    const size_t smem = (size_t)A.scene.n_spheres * 4 * sizeof(float4) + sizeof(long long) * 9 * PT_THREADS + (top ? (size_t)A.top_nodes * 128 + 16 : 0);
     const int grid = n_sms * (blocks_per_sm > 0 ? blocks_per_sm : (A.scene.n_tris > 0 ? PT_MIN_BLOCKS_MESH : PT_MIN_BLOCKS));
     const bool has_tris = A.scene.n_tris > 0;
     if (!has_tris) return count_tests ? launch_variant<false, false, true>(A, grid, smem, stream)
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
+    if (top) return launch_variant<true, false, false, true, true>(A, grid, smem, stream);
     if (A.defer > 0) return count_tests ? launch_variant<true, false, true, true>(A, grid, smem, stream)
                                         : launch_variant<true, false, false, true>(A, grid, smem, stream);
     return count_tests ? launch_variant<true, false, true>(A, grid, smem, stream)

@@ -105,7 +105,7 @@ pathtrace_pool_kernel(const __grid_constant__ RenderArgs A)
     int pend = 0;
     int stack[TRT_STACK_DEPTH];
 
-    unsigned ray_count = 0;
+    unsigned ray_count = 0, skipped = 0;
     TraceCounters cnt; cnt.box_tests = cnt.tri_tests = cnt.sphere_tests = 0;
     unsigned long long sc_trips = 0, sc_inside = 0, sc_node = 0, sc_leaf = 0, sc_sessions = 0, sc_hk = 0, sc_consume = 0;
     unsigned long long* t_start = (unsigned long long*)(hr_ring + PP_RING);
@@ -188,7 +188,7 @@ pathtrace_pool_kernel(const __grid_constant__ RenderArgs A)
                             if (f != 0 && !(A.exp_flags & 4)) atomicAdd((unsigned long long*)(A.accum + (size_t)c * npix + pixel), (unsigned long long)f);
                         }
                     }
-                    if (ended) phase = PH_NEW; else new_ray = true;
+                    if (ended) { phase = PH_NEW; ray_count += res.dead_ao; skipped += res.dead_ao; } else new_ray = true;
                 }
 
                 // A2. slots without a path take the next one of the warp's reservation
@@ -323,6 +323,12 @@ pathtrace_pool_kernel(const __grid_constant__ RenderArgs A)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) rc += __shfl_xor_sync(0xffffffffu, rc, off);
     if (lane == 0 && rc) atomicAdd(A.counters + 0, rc);
+    if (A.use_ao) {
+        unsigned long long sk = skipped;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sk += __shfl_xor_sync(0xffffffffu, sk, off);
+        if (lane == 0 && sk) atomicAdd(A.counters + 11, sk);
+    }
     if (COUNT) {
         unsigned long long b = cnt.box_tests, t = cnt.tri_tests, s = cnt.sphere_tests;
 #pragma unroll

@@ -282,17 +282,26 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
 // several lanes instead of the 3-4 that happen to be at a leaf in any one trip (ncu: a third of all warp instructions at
 // 3.5 lanes).  Nodes visited in between do not see the parked leaf's hit distance yet, so a few more of them are visited;
 // the result is unchanged.  Must be called by all 32 lanes.
-template <bool COUNT>
+// TOP: the first top_k wide nodes (the top levels of the tree: the collapse numbers nodes level by level) were staged into
+// shared memory at kernel start (TMA bulk copy, pathtrace.cu) and are read from there, same rotated layout.
+template <bool COUNT, bool TOP = false>
 __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
                                                   int src_leaf, int twin_leaf, bool any_hit, int share,
-                                                  Trav& tr, int& pend, int* stack, TraceCounters& cnt, int exp_flags = 0)
+                                                  Trav& tr, int& pend, int* stack, TraceCounters& cnt, int exp_flags = 0,
+                                                  const float4* s_top = nullptr, int top_k = 0)
 {
     if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) {
-        const float4* rec = sc.nodes + 8 * (size_t)tr.node;
         const int rot = tr.node & 3;
         float4 f0a, f0b, f1a, f1b, f2a, f2b, f3a, f3b;
-        ldg256(rec + 2 * ((0 + rot) & 3), f0a, f0b); ldg256(rec + 2 * ((1 + rot) & 3), f1a, f1b);
-        ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b); ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
+        if (TOP && tr.node < top_k) {
+            const float4* rec = s_top + 8 * tr.node;
+            f0a = rec[2 * ((0 + rot) & 3)]; f0b = rec[2 * ((0 + rot) & 3) + 1]; f1a = rec[2 * ((1 + rot) & 3)]; f1b = rec[2 * ((1 + rot) & 3) + 1];
+            f2a = rec[2 * ((2 + rot) & 3)]; f2b = rec[2 * ((2 + rot) & 3) + 1]; f3a = rec[2 * ((3 + rot) & 3)]; f3b = rec[2 * ((3 + rot) & 3) + 1];
+        } else {
+            const float4* rec = sc.nodes + 8 * (size_t)tr.node;
+            ldg256(rec + 2 * ((0 + rot) & 3), f0a, f0b); ldg256(rec + 2 * ((1 + rot) & 3), f1a, f1b);
+            ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b); ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
+        }
         const float INF = __int_as_float(0x7f800000);
 #define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
     {                                                                                                      \
@@ -339,25 +348,46 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
             const float4* rec = sc.tri + 4 * (size_t)p;
             float4 f0a, f0b, f1a, f1b;
             ldg256(rec, f0a, f0b); ldg256(rec + 2, f1a, f1b);
+#define TRT_LEAF_TEST(P, R0, R1, R2, R3)                                                                                  \
+    if ((P) != src_leaf && (P) != twin_leaf) {                                                                            \
+        float t, u, v;                                                                                                    \
+        if (COUNT) cnt.tri_tests++;                                                                                       \
+        if (triangle_test(R0, R1, R2, o, d, sc.tri_tmin, t, u, v)) {                                                      \
+            const int ns = sc.n_spheres;                                                                                  \
+            bool take = t < tr.t;                                                                                         \
+            if (t == tr.t && tr.prim >= ns) take = __float_as_int(R3.x) < __ldg(sc.tri_orig + (tr.prim - ns));            \
+            if (take) {                                                                                                   \
+                tr.t = t; tr.prim = ns + (P); tr.u = u; tr.v = v;                                                         \
+                if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; left = 0; }                                            \
+            }                                                                                                             \
+        }                                                                                                                 \
+    }
+#ifdef TRT_LEAF_PAIRS
+            // two triangles of the run per iteration: the runs of the reference's meshes are 2, 4 or 8 long (the halves of a
+            // face, its back faces, crossed plant quads), and the second record's fetch overlaps the first one's test
+            // (the record after the last one of a run is fetched too: the triangle buffer has 256 bytes of slack for that)
+            float4 g0a, g0b, g1a, g1b;
+            ldg256(rec + 4, g0a, g0b); ldg256(rec + 6, g1a, g1b);
             int left = __float_as_int(f1b.w);
             for (;;) {
-                if (p != src_leaf && p != twin_leaf) {
-                    float t, u, v;
-                    if (COUNT) cnt.tri_tests++;
-                    if (triangle_test(f0a, f0b, f1a, o, d, sc.tri_tmin, t, u, v)) {
-                        const int ns = sc.n_spheres;
-                        bool take = t < tr.t;
-                        if (t == tr.t && tr.prim >= ns) take = __float_as_int(f1b.x) < __ldg(sc.tri_orig + (tr.prim - ns));
-                        if (take) {
-                            tr.t = t; tr.prim = ns + p; tr.u = u; tr.v = v;
-                            if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; left = 0; }
-                        }
-                    }
-                }
+                TRT_LEAF_TEST(p, f0a, f0b, f1a, f1b)
+                if (left >= 2) { TRT_LEAF_TEST(p + 1, g0a, g0b, g1a, g1b) }
+                left -= 2;
+                if (left <= 0) break;
+                p += 2; rec += 8;
+                ldg256(rec, f0a, f0b); ldg256(rec + 2, f1a, f1b);
+                ldg256(rec + 4, g0a, g0b); ldg256(rec + 6, g1a, g1b);
+            }
+#else
+            int left = __float_as_int(f1b.w);
+            for (;;) {
+                TRT_LEAF_TEST(p, f0a, f0b, f1a, f1b)
                 if (--left <= 0) break;
                 p++; rec += 4;
                 ldg256(rec, f0a, f0b); ldg256(rec + 2, f1a, f1b);
             }
+#endif
+#undef TRT_LEAF_TEST
         }
     }
 }

@@ -33,6 +33,7 @@ struct RenderArgs {
     int max_hk, hk_min;                 // megakernel: housekeeping passes per trip; repeated while fewer than hk_min/32 of the live lanes have BVH work
     int defer;                          // megakernel: > 0 = deferred leaves, tested once 1/defer of the lanes inside hold one (bvh_trip_deferred)
     int item_order;                     // see decode_item (trt_shade.cuh)
+    int top_nodes;                      // megakernel: this many wide nodes (the top levels) are staged into shared memory by TMA; 0 = off (TRT_TUNE_TOPK)
     int exp_flags;                      // experiments (TRT_TUNE_EXP): 1 = L1 prefetch of a leaf's triangles when it is parked, 2 = of the next node after a visit
     // slot-pool kernel (pathtrace_pool.cu): n_items = paths of this launch, pool = paths a warp reserves per atomic
     int pp_slots;                       // path slots per warp (<= 64)

@@ -24,6 +24,7 @@ struct PathState {
 
 struct PathResult {         // what one finished path adds to its pixel (col_alb_norm, denoiser.h:11-13)
     float3 L, albedo, normal;
+    int dead_ao;            // 1: the path ended on a shaded bounce whose ambient-occlusion ray was counted but not traced (see consume_hit)
 };
 
 // item index -> (pixel slot p of an 8x4 tile, sample chunk, tile).  An item is (pixel, chunk of samples); 32*n_chunks
@@ -104,6 +105,7 @@ __device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* _
 {
     const DevScene& sc = A.scene;
     const bool did_hit = hit_prim != TRT_NO_PRIM;
+    res.dead_ao = 0;
 
     if (phase == PH_AO) {
         // ambient_occlusion (main.c:94-116): distance/dst == 1 for a unit direction, so the term is
@@ -194,9 +196,19 @@ __device__ __forceinline__ bool consume_hit(const RenderArgs& A, const float4* _
         if (P.T.x > 0.5f || P.T.y > 0.5f || P.T.z > 0.5f) P.T = m.diffuse * (P.T * 1.3f);         // main.c:214-216
         P.T = m.diffuse * P.T;
         if (A.use_ao) {
-            P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                             // main.c:100-102
-            if (fuse_ao) { P.ao_pending = true; if (P.bounce >= A.bounces) phase = PH_AO; }       // AO ray rides with the next bounce ray
-            else phase = PH_AO;
+#ifndef TRT_KEEP_DEAD_AO          /* -DTRT_KEEP_DEAD_AO traces it like the reference (for A/B runs: same image, same ray count) */
+            if (P.bounce >= A.bounces) {
+                // last trip of main.c:132: ambient_occlusion (main.c:220-221) only scales rayColor, which nothing reads after the
+                // loop.  The reference traces that ray all the same; here it is COUNTED (trt_stats.rays stays the reference's
+                // closest_hit count, trt_stats.rays_skipped says how many of them were not traced) and the path ends now.
+                res.dead_ao = 1;
+            } else
+#endif
+            {
+                P.d_ao = normalize3(n + unit_sphere(u01(r.z), u01(r.w)));                         // main.c:100-102
+                if (fuse_ao) { P.ao_pending = true; if (P.bounce >= A.bounces) phase = PH_AO; }   // AO ray rides with the next bounce ray
+                else phase = PH_AO;
+            }
         }
     }
     res.L = P.L;

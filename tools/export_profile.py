@@ -9,9 +9,9 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed.avg.per_cycle_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "smsp__sass_thread_inst_executed_op_ffma_pred_on.sum", "smsp__sass_thread_inst_executed_op_fadd_pred_on.sum",
-        "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum",
+        "smsp__sass_thread_inst_executed_op_fmul_pred_on.sum", "smsp__sass_thread_inst_executed_op_fp32_pred_on.sum",
         "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
-        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "lts__t_bytes.sum", "lts__t_sectors_op_red.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "smsp__warps_eligible.avg.per_cycle_active",
         "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct", "smsp__warp_issue_stalled_wait_per_warp_active.pct",
         "smsp__warp_issue_stalled_branch_resolving_per_warp_active.pct", "smsp__warp_issue_stalled_math_pipe_throttle_per_warp_active.pct",
@@ -27,6 +27,14 @@ for r in rows[2:]:
         if k in hdr:
             i = hdr.index(k)
             lines.append(f"| {k} | {r[i]} | {units[i]} |")
+    # SURVEY §8d cross-check: FLOP/s from the executed FP32 instructions (FFMA = 2) next to the algorithmic F_ray figure of bench.py
+    try:
+        g = lambda k: float(r[hdr.index(k)])
+        fl = 2 * g("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum") + g("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum") + g("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum")
+        ms = g("gpu__time_duration.sum") * {"ms": 1.0, "us": 1e-3, "msecond": 1.0, "usecond": 1e-3, "ns": 1e-6, "nsecond": 1e-6, "second": 1e3, "s": 1e3}.get(units[hdr.index("gpu__time_duration.sum")], 1.0)
+        lines.append(f"| FP32 FLOP from FFMA x2 + FADD + FMUL | {fl/1e9:.1f} GFLOP = {fl/ms/1e9:.2f} TFLOP/s = {fl/ms/1e9/74.45*100:.1f} % of 74.45 TFLOP/s | derived |")
+    except Exception:
+        pass
     lines.append("")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
