@@ -174,3 +174,40 @@ def test_tile_parts_assemble_the_image(rt):
         assert 0.2 < touched < 0.5                                   # a third of the tiles (sky / black pixels stay zero anyway)
     with pytest.raises(trt.TrtError):
         rt.accumulate(dataclasses.replace(rp, tile_part=5 | (3 << 16)), acc.data_ptr())
+
+
+def test_render_distributed_single_rank_equals_render(rt):
+    """trt_render_distributed with one rank (no communicator) is trt_render; its stats describe the rank's share."""
+    sc = S.cornell_spheres()
+    rt.scene_set(sc)
+    rp = S.params_for(sc, width=120, spp=9)
+    a = rt.render(rp)
+    b = rt.render_distributed(rp, 0, 0, 1)
+    for k in ("canva", "albedo", "normal"):
+        assert a[k].tobytes() == b[k].tobytes()
+    assert a["stats"]["rays"] == b["stats"]["rays"] and b["stats"]["paths"] == rp.width * rp.height * rp.spp
+    # the AO ray of a path's last bounce is counted like the reference counts it, but not traced (trt_stats.rays_skipped)
+    assert 0 < a["stats"]["rays_skipped"] <= a["stats"]["paths"] and a["stats"]["rays_skipped"] < a["stats"]["rays"]
+    with pytest.raises(trt.TrtError):
+        rt.render_distributed(rp, 0, 1, 2)                      # two ranks need a communicator
+    assert rt.lib.trt_nccl_version() >= 20000                    # NCCL is found at run time (libnccl.so.2)
+
+
+def test_c_host_program_one_process_per_gpu(rt, tmp_path):
+    """apps/main_b200 --nranks 2: two PROCESSES, one GPU each, the NCCL id handed over through a file, ncclReduce inside
+    libtipe_rt.so (no Python, no torch.distributed on the data path).  Same image as one process on one GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "apps"), "main_b200"], stderr=subprocess.DEVNULL)
+    exe = os.path.join(ROOT, "apps", "main_b200")
+    common = ["--width", "200", "--spp", "30", "--bounces", "5"]
+    one = str(tmp_path / "one.ppm")
+    subprocess.check_call([exe, *common, "--out", one], stdout=subprocess.DEVNULL)
+    for extra, name in (([], "two.ppm"), (["--tile-split"], "two_tiles.ppm")):
+        out = str(tmp_path / name)
+        idf = str(tmp_path / (name + ".id"))
+        procs = [subprocess.Popen([exe, *common, *extra, "--nranks", "2", "--rank", str(r), "--id-file", idf, "--out", out],
+                                  stdout=subprocess.DEVNULL) for r in (1, 0)]
+        assert [p.wait(timeout=120) for p in procs] == [0, 0]
+        assert open(out).read() == open(one).read()

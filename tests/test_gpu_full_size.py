@@ -112,7 +112,7 @@ def test_c4big_one_million_triangles(rt, oracle):
     print(f"C4big {mid.width}x{mid.height}: {flips} of {exact['id'].shape[0]} first-hit ids differ between the FP64 scan and the FP32 BVH walk; "
           f"{(exact['id'] >= 1).mean():.3f} of the pixels see a triangle; bvh {info}")
     # 576 trees of thin double-sided leaf quads seen from far away: many more silhouettes per pixel than C4 (1.9e-6 there); observed 11 / 129 600
-    assert flips <= 2e-4 * exact["id"].shape[0] and (exact["id"] >= 1).mean() > 0.3
+    assert flips <= 2e-4 * exact["id"].shape[0] and (exact["id"] >= 1).mean() > 0.03      # the camera is pulled back to see all 576 trees
     rp = S.params_for(sc, width=960, spp=12)
     full, st = _accumulate(rt, rp)
     parts = torch.zeros_like(full)

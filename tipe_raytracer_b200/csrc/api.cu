@@ -116,7 +116,7 @@ int ensure_out(trt_ctx* ctx, DeviceCtx& d, size_t npix)
     if (d.out_px >= npix) return TRT_OK;
     if (d.out) cudaFree(d.out);
     d.out = nullptr; d.out_px = 0;
-    CU(ctx, cudaMalloc(&d.out, sizeof(double) * 9 * npix));
+    CU(ctx, cudaMalloc(&d.out, sizeof(double) * 9 * npix + 512));      // 9 doubles per pixel, or the compact layout of copy_out (256-byte padding)
     d.out_px = npix;
     return TRT_OK;
 }
@@ -141,39 +141,59 @@ void ensure_stage(DeviceCtx& d, size_t bytes)
     }
 }
 
-// d.out (canva | albedo | normal, 3*npix doubles each) -> the caller's three arrays, then waits for the stream.
+// Layout of d.out when the three arrays go to the HOST: canva as 3 BYTES per pixel (the values are integers 0..255: exact, and
+// 21 of the 72 bytes a pixel costs over PCIe stay home), padded to 256 bytes, then albedo and normal as 3 doubles per pixel.
+size_t canva8_bytes(size_t npix) { return (3 * npix + 255) & ~(size_t)255; }
+
+// d.out -> the caller's three arrays (canva widened to doubles on the way), then waits for the stream.
 int copy_out(trt_ctx* ctx, DeviceCtx& d, size_t npix, trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab)
 {
-    const size_t part = sizeof(double) * 3 * npix, total = 3 * part;
-    const size_t n_chunks = (total + COPY_CHUNK - 1) / COPY_CHUNK;
-    const bool staged = canva && albedo_tab && normal_tab && d.h_stage && d.stage_bytes >= total && d.chunk_ev.size() >= n_chunks && total >= 4 * COPY_CHUNK;
+    const size_t c8 = canva8_bytes(npix), part = sizeof(double) * 3 * npix, total = c8 + 2 * part;
+    const size_t n_chunks = 1 + (2 * part + COPY_CHUNK - 1) / COPY_CHUNK;
+    const bool staged = d.h_stage && d.stage_bytes >= total && d.chunk_ev.size() >= n_chunks && total >= 4 * COPY_CHUNK;
+    const char* src = (const char*)d.out;
+    auto widen = [](double* dst, const unsigned char* s8, size_t count) { for (size_t k = 0; k < count; k++) dst[k] = (double)s8[k]; };
     if (!staged) {
-        if (canva) CU(ctx, cudaMemcpyAsync(canva, d.out, part, cudaMemcpyDeviceToHost, d.stream));
-        if (albedo_tab) CU(ctx, cudaMemcpyAsync(albedo_tab, d.out + 3 * npix, part, cudaMemcpyDeviceToHost, d.stream));
-        if (normal_tab) CU(ctx, cudaMemcpyAsync(normal_tab, d.out + 6 * npix, part, cudaMemcpyDeviceToHost, d.stream));
+        std::vector<unsigned char> tmp(canva ? 3 * npix : 0);
+        if (canva) CU(ctx, cudaMemcpyAsync(tmp.data(), src, 3 * npix, cudaMemcpyDeviceToHost, d.stream));
+        if (albedo_tab) CU(ctx, cudaMemcpyAsync(albedo_tab, src + c8, part, cudaMemcpyDeviceToHost, d.stream));
+        if (normal_tab) CU(ctx, cudaMemcpyAsync(normal_tab, src + c8 + part, part, cudaMemcpyDeviceToHost, d.stream));
         CU(ctx, cudaStreamSynchronize(d.stream));
+        if (canva) widen((double*)canva, tmp.data(), 3 * npix);
         return TRT_OK;
     }
-    for (size_t c = 0; c < n_chunks; c++) {
-        const size_t off = c * COPY_CHUNK, len = (off + COPY_CHUNK <= total) ? COPY_CHUNK : total - off;
-        CU(ctx, cudaMemcpyAsync(d.h_stage + off, (const char*)d.out + off, len, cudaMemcpyDeviceToHost, d.stream));
-        CU(ctx, cudaEventRecord(d.chunk_ev[c], d.stream));
+    // chunk 0 = the canva bytes (they arrive first and every thread widens a slice of them), chunks 1.. = 2 MB pieces of the two AOV tables
+    const size_t n_aov = (2 * part + COPY_CHUNK - 1) / COPY_CHUNK;
+    CU(ctx, cudaMemcpyAsync(d.h_stage, src, c8, cudaMemcpyDeviceToHost, d.stream));
+    CU(ctx, cudaEventRecord(d.chunk_ev[0], d.stream));
+    for (size_t c = 0; c < n_aov; c++) {
+        const size_t off = c8 + c * COPY_CHUNK, len = (c + 1) * COPY_CHUNK <= 2 * part ? COPY_CHUNK : 2 * part - c * COPY_CHUNK;
+        CU(ctx, cudaMemcpyAsync(d.h_stage + off, src + off, len, cudaMemcpyDeviceToHost, d.stream));
+        CU(ctx, cudaEventRecord(d.chunk_ev[1 + c], d.stream));
     }
-    char* dst[3] = {(char*)canva, (char*)albedo_tab, (char*)normal_tab};
-    int n_threads = 8;                                          // measured on the B200 box's host: 2 threads 2.7 ms, 4: 2.1, 8: 1.4, 12: 1.4 for 54 MB
+    // the host side (bytes -> doubles, staging -> the caller's pageable arrays) is the slow half, not PCIe; measured on the B200 box's
+    // 16-core host for C2's 750 000 pixels: 1 thread 5.6 ms, 2: 3.0, 4: 2.0, 8: 1.3, 16: 1.15
+    int n_threads = 16;
     { const unsigned hc = std::thread::hardware_concurrency(); if (hc > 0 && (int)hc < n_threads) n_threads = (int)hc; }
     { const char* v = getenv("TRT_TUNE_COPY_THREADS"); if (v && *v) n_threads = atoi(v); }
     if (n_threads < 1) n_threads = 1;
     if (n_threads > 16) n_threads = 16;
     cudaError_t errs[16];
+    char* aov_dst[2] = {(char*)albedo_tab, (char*)normal_tab};
     auto worker = [&](int t) {
         errs[t] = cudaSetDevice(d.dev);
-        for (size_t c = (size_t)t; c < n_chunks && errs[t] == cudaSuccess; c += (size_t)n_threads) {
-            errs[t] = cudaEventSynchronize(d.chunk_ev[c]);
-            size_t off = c * COPY_CHUNK, end = (off + COPY_CHUNK <= total) ? off + COPY_CHUNK : total;
-            while (off < end && errs[t] == cudaSuccess) {          // a chunk may straddle two of the caller's arrays
+        if (errs[t] == cudaSuccess) errs[t] = cudaEventSynchronize(d.chunk_ev[0]);
+        if (errs[t] == cudaSuccess && canva) {
+            const size_t n8 = 3 * npix, lo = n8 * (size_t)t / (size_t)n_threads, hi = n8 * (size_t)(t + 1) / (size_t)n_threads;
+            widen((double*)canva + lo, (const unsigned char*)d.h_stage + lo, hi - lo);
+        }
+        for (size_t c = (size_t)t; c < n_aov && errs[t] == cudaSuccess; c += (size_t)n_threads) {
+            errs[t] = cudaEventSynchronize(d.chunk_ev[1 + c]);
+            size_t off = c * COPY_CHUNK;
+            const size_t end = (c + 1) * COPY_CHUNK <= 2 * part ? (c + 1) * COPY_CHUNK : 2 * part;
+            while (off < end && errs[t] == cudaSuccess) {          // a chunk may straddle the two tables
                 const size_t a = off / part, in = off - a * part, len = (end - off < part - in) ? end - off : part - in;
-                memcpy(dst[a] + in, d.h_stage + off, len);
+                if (aov_dst[a]) memcpy(aov_dst[a] + in, d.h_stage + c8 + off, len);
                 off += len;
             }
         }
@@ -742,7 +762,7 @@ TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_ac
 }
 
 static int resolve_common(trt_ctx* ctx, const trt_params* p, const long long* const* srcs, int n_src,
-                          double* d_canva, double* d_albedo, double* d_normal)
+                          double* d_canva, double* d_albedo, double* d_normal, unsigned char* d_canva8 = nullptr)
 {
     DeviceCtx& d = ctx->devs[0];
     ResolveArgs R{};
@@ -750,7 +770,7 @@ static int resolve_common(trt_ctx* ctx, const trt_params* p, const long long* co
     R.divisor = p->sample_total > 0 ? p->sample_total : p->nbRayonParPixel;
     R.n_src = n_src;
     for (int k = 0; k < n_src; k++) R.src[k] = srcs[k];
-    R.canva = d_canva; R.albedo = d_albedo; R.normal = d_normal;
+    R.canva = d_canva; R.albedo = d_albedo; R.normal = d_normal; R.canva8 = d_canva8;
     CU(ctx, trt_launch_resolve(R, d.n_sms, d.stream));
     return TRT_OK;
 }
@@ -780,7 +800,8 @@ TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d
     CU(ctx, cudaSetDevice(d.dev));
     if ((rc = ensure_out(ctx, d, npix)) != TRT_OK) return rc;
     const long long* src = (const long long*)d_accum;
-    rc = resolve_common(ctx, params, &src, 1, d.out, d.out + 3 * npix, d.out + 6 * npix);
+    char* ob = (char*)d.out;
+    rc = resolve_common(ctx, params, &src, 1, nullptr, (double*)(ob + canva8_bytes(npix)), (double*)(ob + canva8_bytes(npix)) + 3 * npix, (unsigned char*)ob);
     if (rc != TRT_OK) return rc;
     if (canva && albedo_tab && normal_tab) ensure_stage(d, sizeof(double) * 9 * npix);
     return copy_out(ctx, d, npix, canva, albedo_tab, normal_tab);
@@ -863,7 +884,8 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
     for (int k = 1; k < n_dev; k++) CU(ctx, cudaStreamWaitEvent(root.stream, ctx->devs[k].ev_c, 0));
     trt_params rp = *params;
     if (rp.sample_total <= 0) rp.sample_total = spp;
-    if ((rc = resolve_common(ctx, &rp, srcs.data(), n_dev, root.out, root.out + 3 * npix, root.out + 6 * npix)) != TRT_OK) return rc;
+    char* ob = (char*)root.out;
+    if ((rc = resolve_common(ctx, &rp, srcs.data(), n_dev, nullptr, (double*)(ob + canva8_bytes(npix)), (double*)(ob + canva8_bytes(npix)) + 3 * npix, (unsigned char*)ob)) != TRT_OK) return rc;
     launches++;
     CU(ctx, cudaEventRecord(root.ev_d, root.stream));
     if ((rc = copy_out(ctx, root, npix, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;
@@ -920,7 +942,8 @@ TRT_API int trt_render_distributed(trt_ctx* ctx, const trt_params* params, void*
         trt_params rp = *params;
         if (rp.sample_total <= 0) rp.sample_total = spp;
         const long long* src = d.accum;
-        if ((rc = resolve_common(ctx, &rp, &src, 1, d.out, d.out + 3 * npix, d.out + 6 * npix)) != TRT_OK) return rc;
+        char* ob = (char*)d.out;
+        if ((rc = resolve_common(ctx, &rp, &src, 1, nullptr, (double*)(ob + canva8_bytes(npix)), (double*)(ob + canva8_bytes(npix)) + 3 * npix, (unsigned char*)ob)) != TRT_OK) return rc;
         launches++;
         CU(ctx, cudaEventRecord(d.ev_d, d.stream));
         if ((rc = copy_out(ctx, d, npix, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;

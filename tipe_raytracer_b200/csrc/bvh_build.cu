@@ -140,10 +140,11 @@ __global__ void morton_keys(int n, const float4* __restrict__ box_lo, const floa
 // Triangles in leaf order.  N = AB x AC is formed in FP64 and rounded once.
 __global__ void emit_leaves(int n, const unsigned long long* __restrict__ keys, const double* __restrict__ raw,
                             const int* __restrict__ quel_mat, const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
-                            float pad, float4* tri, float4* tri_uv, int* tri_orig, float4* leaf_lo, float4* leaf_hi)
+                            const int* __restrict__ bounds, float4* tri, float4* tri_uv, int* tri_orig, float4* leaf_lo, float4* leaf_hi)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
+    const float pad = __fadd_rn(__fmul_rn(ord2f(bounds[6]), 4.76837158e-7f), 1e-30f);          // 2^-21 of the largest |coordinate| (host: trt_build_scene)
     const int k = (int)(keys[p] & IDX_MASK);
     const double* t = raw + 25 * (size_t)k;
     const double ab[3] = {t[3] - t[0], t[4] - t[1], t[5] - t[2]}, ac[3] = {t[6] - t[0], t[7] - t[1], t[8] - t[2]};
@@ -190,8 +191,9 @@ __global__ void group_first(int n, const int* __restrict__ head, const int* __re
 }
 
 // the head record of every leaf carries the number of triangles of the run
-__global__ void group_counts(int n_groups, int n, const int* __restrict__ gfirst, float4* tri)
+__global__ void group_counts(int n, const int* __restrict__ ghead, const int* __restrict__ gpos, const int* __restrict__ gfirst, float4* tri)
 {
+    const int n_groups = gpos[n - 1] + ghead[n - 1];
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
     const int first = gfirst[g], next = (g + 1 < n_groups) ? gfirst[g + 1] : n;
@@ -380,15 +382,13 @@ __global__ void sah_cost_kernel(int n, const int2* __restrict__ children, const 
     if ((threadIdx.x & 31) == 0 && cost != 0.0) atomicAdd(sah, cost);
 }
 
-// One level of the binary -> 4-wide collapse.  q_in[k] = (binary node, wide node index to fill).
-// counters[0] = wide nodes allocated so far, counters[1] = entries written to q_out.
-__global__ void collapse_level(const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                               const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
-                               const int2* __restrict__ q_in, int n_in, int2* q_out, int* counters, float4* nodes4)
+// One entry of the binary -> 4-wide collapse: e = (binary node, wide node index to fill).  The node adopts its grandchildren,
+// largest box first, until it has 4 children.  counters[0] = wide nodes allocated so far, counters[1] = entries written to q_out
+// (global or shared memory).  children / node_lo / node_hi carry no __restrict__: build_small_kernel writes them earlier in the same
+// kernel, and a non-coherent (LDG.CONSTANT) read would be allowed to miss those writes.
+__device__ __forceinline__ void collapse_entry(int2 e, const int2* children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                                               const float4* node_lo, const float4* node_hi, int2* q_out, int* counters, float4* nodes4)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_in) return;
-    const int2 e = q_in[k];
     int c[4]; int nc = 2;
     { const int2 ch = children[e.x]; c[0] = ch.x; c[1] = ch.y; c[2] = c[3] = 0; }
     while (nc < 4) {
@@ -427,6 +427,153 @@ __global__ void collapse_level(const int2* __restrict__ children, const float4* 
     f2[0] = make_float4(lo[2][0], lo[2][1], lo[2][2], lo[2][3]); f2[1] = make_float4(hi[2][0], hi[2][1], hi[2][2], hi[2][3]);
     f3[0] = make_float4(__int_as_float(ref[0]), __int_as_float(ref[1]), __int_as_float(ref[2]), __int_as_float(ref[3]));
     f3[1] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// One level of the collapse, one launch per level (large scenes).
+__global__ void collapse_level(const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
+                               const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
+                               const int2* __restrict__ q_in, int n_in, int2* q_out, int* counters, float4* nodes4)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_in) return;
+    collapse_entry(q_in[k], children, leaf_lo, leaf_hi, node_lo, node_hi, q_out, counters, nodes4);
+}
+
+// ---- small scenes: hierarchy, SAH report and collapse in ONE CTA, no host round trip ---------------------------------
+// Up to SMALL_MAX_GROUPS leaves (every mesh of the reference: 2 035 on C2, 895 on C4).  PLOC exactly as above (same nearest /
+// merge / compact passes, same tie rules), but the clusters live in shared memory, the passes are separated by __syncthreads()
+// instead of kernel boundaries, and the loop ends on the device.  The multi-kernel path needs ~100 launches and ~10 host
+// read-backs for C2 (1.5 ms of a 1.7 ms trt_scene_set); this one is a single launch.
+constexpr int SMALL_MAX_GROUPS = 4096;
+constexpr int SMALL_THREADS = 1024;
+struct SmallResult { int root, n_wide, wide_depth, n_groups; double sah; };
+
+__global__ void __launch_bounds__(SMALL_THREADS, 1)
+build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__ gpos, const int* __restrict__ gfirst,
+                   const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int radius,
+                   int2* children, float4* node_lo, float4* node_hi, int2* queue_a, int2* queue_b, float4* nodes4, SmallResult* result)
+{
+    extern __shared__ float4 sm4[];
+    const int n_groups = gpos[n - 1] + ghead[n - 1];
+    if (n_groups > SMALL_MAX_GROUPS) { if (threadIdx.x == 0) result->n_groups = n_groups; return; }     // host falls back to the multi-kernel path
+    float4* clo = sm4;                                      // [SMALL_MAX_GROUPS] cluster boxes, in Morton order
+    float4* chi = clo + SMALL_MAX_GROUPS;
+    int* cid = (int*)(chi + SMALL_MAX_GROUPS);              // leaf ~p or internal node
+    int* nn = cid + SMALL_MAX_GROUPS;
+    __shared__ int s_warp[32];
+    __shared__ int s_count, s_nodes, s_counters[2];
+    __shared__ double s_sah[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int g = tid; g < n_groups; g += SMALL_THREADS) { const int p = gfirst[g]; cid[g] = ~p; clo[g] = leaf_lo[p]; chi[g] = leaf_hi[p]; }
+    if (tid == 0) { s_count = n_groups; s_nodes = 0; }
+    __syncthreads();
+    int root = ~0;
+    if (n_groups > 1) {
+        int c = n_groups;
+        while (c > 1) {
+            // nearest neighbour within the search radius (ties: lowest index)
+            for (int i = tid; i < c; i += SMALL_THREADS) {
+                const float4 lo = clo[i], hi = chi[i];
+                float best = 3.0e38f; int bj = -1;
+                const int j0 = max(0, i - radius), j1 = min(c - 1, i + radius);
+                for (int j = j0; j <= j1; j++) {
+                    if (j == i) continue;
+                    const float4 l2 = clo[j], h2 = chi[j];
+                    const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+                    const float a = dx * dy + dy * dz + dz * dx;
+                    if (a < best) { best = a; bj = j; }
+                }
+                nn[i] = bj;
+            }
+            __syncthreads();
+            // merge mutual pairs (the lower index keeps the merged cluster), then compact: every thread owns a contiguous chunk
+            const int per = (c + SMALL_THREADS - 1) / SMALL_THREADS;          // <= 4
+            const int first = tid * per;
+            int k_id[4]; float4 k_lo[4], k_hi[4]; int kept = 0;
+            for (int q = 0; q < per; q++) {
+                const int i = first + q;
+                if (i >= c) break;
+                const int j = nn[i];
+                int id = cid[i]; float4 lo = clo[i], hi = chi[i];
+                bool keep = true;
+                if (j >= 0 && nn[j] == i) {
+                    if (i < j) {
+                        const int node = atomicAdd(&s_nodes, 1);
+                        const float4 l2 = clo[j], h2 = chi[j];
+                        lo = make_float4(fminf(lo.x, l2.x), fminf(lo.y, l2.y), fminf(lo.z, l2.z), 0.0f);
+                        hi = make_float4(fmaxf(hi.x, h2.x), fmaxf(hi.y, h2.y), fmaxf(hi.z, h2.z), 0.0f);
+                        children[node] = make_int2(id, cid[j]);
+                        node_lo[node] = lo; node_hi[node] = hi;
+                        id = node;
+                    } else keep = false;
+                }
+                if (keep) { k_id[kept] = id; k_lo[kept] = lo; k_hi[kept] = hi; kept++; }
+            }
+            // exclusive scan of `kept` over the block
+            int incl = kept;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += y; }
+            if (lane == 31) s_warp[warp] = incl;
+            __syncthreads();                                  // also: every thread has read its chunk (and its partners' boxes) by now
+            if (warp == 0) {
+                int w = s_warp[lane];
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += y; }
+                s_warp[lane] = w;
+                if (lane == 31) s_count = w;
+            }
+            __syncthreads();
+            const int base = (warp > 0 ? s_warp[warp - 1] : 0) + incl - kept;
+            for (int q = 0; q < kept; q++) { cid[base + q] = k_id[q]; clo[base + q] = k_lo[q]; chi[base + q] = k_hi[q]; }
+            c = s_count;
+            __syncthreads();
+        }
+        root = cid[0];
+    }
+    __syncthreads();
+    const int n_inner = n_groups - 1;
+
+    // SAH report (same formula as sah_cost_kernel)
+    double cost = 0.0;
+    if (n_inner > 0) {
+        const float root_area = fmaxf(half_area(node_lo[root], node_hi[root]), 1e-30f);
+        for (int i = tid; i < n_inner; i += SMALL_THREADS) {
+            const int2 ch = children[i];
+            cost += (double)(half_area(node_lo[i], node_hi[i]) / root_area) * 2.0;
+            if (ch.x < 0) cost += (double)(half_area(leaf_lo[~ch.x], leaf_hi[~ch.x]) / root_area);
+            if (ch.y < 0) cost += (double)(half_area(leaf_lo[~ch.y], leaf_hi[~ch.y]) / root_area);
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, off);
+    if (lane == 0) s_sah[warp] = cost;
+
+    // binary -> 4-wide, level by level; the queues ping-pong in global scratch
+    int n_in = 0, level = 0;
+    if (tid == 0) { s_counters[0] = 1; s_counters[1] = 0; if (n_inner > 0) queue_a[0] = make_int2(root, 0); }
+    __syncthreads();
+    n_in = n_inner > 0 ? 1 : 0;
+    while (n_in > 0) {
+        const int2* q_in = (level & 1) ? queue_b : queue_a;
+        int2* q_out = (level & 1) ? queue_a : queue_b;
+        for (int k = tid; k < n_in; k += SMALL_THREADS) collapse_entry(q_in[k], children, leaf_lo, leaf_hi, node_lo, node_hi, q_out, s_counters, nodes4);
+        __syncthreads();
+        n_in = s_counters[1];
+        __syncthreads();
+        if (tid == 0) s_counters[1] = 0;
+        __syncthreads();
+        level++;
+    }
+    if (tid == 0) {
+        double total = 0.0;
+        for (int w = 0; w < SMALL_THREADS / 32; w++) total += s_sah[w];
+        result->root = n_inner > 0 ? 0 : ~0;
+        result->n_wide = n_inner > 0 ? s_counters[0] : 0;
+        result->wide_depth = level;
+        result->n_groups = n_groups;
+        result->sah = total;
+    }
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -533,7 +680,48 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     group_first<<<grid_n, TB, 0, stream>>>(n, ghead, gpos, gfirst);
     BT(cudaGetLastError());
 
-    // scene scale -> box padding and the FP32 distance threshold
+    emit_leaves<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, in.quel_mat, box_lo, box_hi, small,
+                                          out.tri, out.tri_uv, out.tri_orig, leaf_lo, leaf_hi);
+    find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, out.tri, small + 9);
+    group_counts<<<grid_n, TB, 0, stream>>>(n, ghead, gpos, gfirst, out.tri);
+    BT(cudaGetLastError());
+
+    auto ord2f_h = [](int i) { int b = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &b, 4); return f; };
+    auto scene_scale = [&](const int* h_bounds) {       // box padding and the FP32 distance threshold from the scene's size
+        const float amax = ord2f_h(h_bounds[6]);
+        const float pad = amax * 4.76837158e-7f + 1e-30f;                    // 2^-21 relative
+        out.tri_tmin = fmaxf(1e-7f, amax * 9.53674316e-7f);                  // 2^-20 relative
+        out.root_lo = make_float3(ord2f_h(h_bounds[0]) - pad, ord2f_h(h_bounds[1]) - pad, ord2f_h(h_bounds[2]) - pad);
+        out.root_hi = make_float3(ord2f_h(h_bounds[3]) + pad, ord2f_h(h_bounds[4]) + pad, ord2f_h(h_bounds[5]) + pad);
+    };
+
+    // ---- small scenes: the rest of the build is ONE launch, and the host reads everything back once -------------------
+    const char* small_env = getenv("TRT_TUNE_SMALL_BUILD");
+    if (!lbvh && n <= 4 * SMALL_MAX_GROUPS && !(small_env && *small_env && atoi(small_env) == 0)) {
+        const char* rad = getenv("TRT_TUNE_PLOC_RADIUS");
+        const int radius = rad && *rad ? atoi(rad) : 64;
+        SmallResult* d_res = (SmallResult*)(small + 32);
+        const size_t smem = (size_t)SMALL_MAX_GROUPS * (2 * sizeof(float4) + 2 * sizeof(int));
+        static bool attr_set = false;
+        if (!attr_set) { BT(cudaFuncSetAttribute(build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        build_small_kernel<<<1, SMALL_THREADS, smem, stream>>>(n, ghead, gpos, gfirst, leaf_lo, leaf_hi, radius, children, node_lo, node_hi,
+                                                                (int2*)(base + o_queue_a), (int2*)(base + o_queue_b), out.nodes, d_res);
+        BT(cudaGetLastError());
+        int h_small2[64];
+        BT(cudaMemcpyAsync(h_small2, small, sizeof h_small2, cudaMemcpyDeviceToHost, stream));
+        BT(cudaStreamSynchronize(stream));
+        SmallResult res;
+        memcpy(&res, h_small2 + 32, sizeof res);
+        if (res.n_groups >= 1 && res.n_groups <= SMALL_MAX_GROUPS) {
+            scene_scale(h_small2);
+            out.n_groups = res.n_groups; out.root = res.root; out.n_wide_nodes = res.n_wide; out.wide_depth = res.wide_depth;
+            out.max_depth = res.n_groups > 1 ? res.wide_depth + 1 : 1;
+            out.n_twins = h_small2[9]; out.sah_cost = res.sah;
+            return cudaSuccess;
+        }
+        // more distinct boxes than the single CTA holds: the kernel left at once, the multi-kernel path below takes over
+    }
+
     int h_bounds[8], h_grp[2];
     BT(cudaMemcpyAsync(h_bounds, small, sizeof(int) * 8, cudaMemcpyDeviceToHost, stream));
     BT(cudaMemcpyAsync(h_grp, gpos + n - 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -541,18 +729,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     BT(cudaStreamSynchronize(stream));
     const int n_groups = h_grp[0] + h_grp[1];
     if (n_groups < 1 || n_groups > n) return cudaErrorUnknown;
-    auto ord2f_h = [](int i) { int b = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &b, 4); return f; };
-    const float amax = ord2f_h(h_bounds[6]);
-    const float pad = amax * 4.76837158e-7f + 1e-30f;                    // 2^-21 relative
-    out.tri_tmin = fmaxf(1e-7f, amax * 9.53674316e-7f);                  // 2^-20 relative
-    out.root_lo = make_float3(ord2f_h(h_bounds[0]) - pad, ord2f_h(h_bounds[1]) - pad, ord2f_h(h_bounds[2]) - pad);
-    out.root_hi = make_float3(ord2f_h(h_bounds[3]) + pad, ord2f_h(h_bounds[4]) + pad, ord2f_h(h_bounds[5]) + pad);
-
-    emit_leaves<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, in.quel_mat, box_lo, box_hi, pad,
-                                          out.tri, out.tri_uv, out.tri_orig, leaf_lo, leaf_hi);
-    find_twins<<<grid_n, TB, 0, stream>>>(n, keys_b, in.tris_raw, out.tri_uv, out.tri, small + 9);
-    group_counts<<<(n_groups + TB - 1) / TB, TB, 0, stream>>>(n_groups, n, gfirst, out.tri);
-    BT(cudaGetLastError());
+    scene_scale(h_bounds);
     out.n_groups = n_groups;
     if (n_groups == 1) {
         out.root = ~0; out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;

@@ -293,7 +293,8 @@ resolve_kernel(ResolveArgs R)
             float r = sqrtf((float)(rapport * sum));                 // sqrtf: FLOAT square root, like the reference
             double cl = (double)r;
             cl = cl < 0.0 ? 0.0 : (cl > 0.999 ? 0.999 : cl);         // NaN falls through both tests, as in clamp()
-            R.canva[3 * p + c] = (double)(int)(256.0 * cl);
+            if (R.canva8) R.canva8[3 * p + c] = (unsigned char)(int)(256.0 * cl);
+            else R.canva[3 * p + c] = (double)(int)(256.0 * cl);
             R.albedo[3 * p + c] = ((double)s[3 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
             R.normal[3 * p + c] = ((double)s[6 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
         }

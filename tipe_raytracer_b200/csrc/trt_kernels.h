@@ -52,6 +52,7 @@ struct ResolveArgs {
     int W, H, divisor, n_src;
     const long long* src[TRT_MAX_RESOLVE_SOURCES];
     double *canva, *albedo, *normal;    // [W*H][3]
+    unsigned char* canva8;              // when set, canva is written here as 3 bytes per pixel instead (exact: the values are integers 0..255)
 };
 
 cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_sm, bool brute, bool count_tests, cudaStream_t stream);
