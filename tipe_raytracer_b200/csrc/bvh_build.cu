@@ -387,7 +387,8 @@ __global__ void sah_cost_kernel(int n, const int2* __restrict__ children, const 
 // (global or shared memory).  children / node_lo / node_hi carry no __restrict__: build_small_kernel writes them earlier in the same
 // kernel, and a non-coherent (LDG.CONSTANT) read would be allowed to miss those writes.
 __device__ __forceinline__ void collapse_entry(int2 e, const int2* children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
-                                               const float4* node_lo, const float4* node_hi, int2* q_out, int* counters, float4* nodes4)
+                                               const float4* node_lo, const float4* node_hi, int2* q_out, int* counters, float4* nodes4,
+                                               const float4* __restrict__ tri)
 {
     int c[4]; int nc = 2;
     { const int2 ch = children[e.x]; c[0] = ch.x; c[1] = ch.y; c[2] = c[3] = 0; }
@@ -404,7 +405,7 @@ __device__ __forceinline__ void collapse_entry(int2 e, const int2* children, con
         if (j < nc) {
             const float4 l = c[j] < 0 ? leaf_lo[~c[j]] : node_lo[c[j]], h = c[j] < 0 ? leaf_hi[~c[j]] : node_hi[c[j]];
             lo[0][j] = l.x; lo[1][j] = l.y; lo[2][j] = l.z; hi[0][j] = h.x; hi[1][j] = h.y; hi[2][j] = h.z;
-            if (c[j] < 0) ref[j] = c[j];
+            if (c[j] < 0) ref[j] = TRT_LEAF_REF(~c[j], __float_as_int(tri[4 * (size_t)(~c[j]) + 3].w));      // run length from the head record (group_counts)
             else {
                 const int idx = atomicAdd(counters + 0, 1);
                 ref[j] = idx;
@@ -432,11 +433,11 @@ __device__ __forceinline__ void collapse_entry(int2 e, const int2* children, con
 // One level of the collapse, one launch per level (large scenes).
 __global__ void collapse_level(const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                                const float4* __restrict__ node_lo, const float4* __restrict__ node_hi,
-                               const int2* __restrict__ q_in, int n_in, int2* q_out, int* counters, float4* nodes4)
+                               const int2* __restrict__ q_in, int n_in, int2* q_out, int* counters, float4* nodes4, const float4* __restrict__ tri)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_in) return;
-    collapse_entry(q_in[k], children, leaf_lo, leaf_hi, node_lo, node_hi, q_out, counters, nodes4);
+    collapse_entry(q_in[k], children, leaf_lo, leaf_hi, node_lo, node_hi, q_out, counters, nodes4, tri);
 }
 
 // ---- small scenes: hierarchy, SAH report and collapse in ONE CTA, no host round trip ---------------------------------
@@ -451,7 +452,8 @@ struct SmallResult { int root, n_wide, wide_depth, n_groups; double sah; };
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
 build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__ gpos, const int* __restrict__ gfirst,
                    const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int radius,
-                   int2* children, float4* node_lo, float4* node_hi, int2* queue_a, int2* queue_b, float4* nodes4, SmallResult* result)
+                   int2* children, float4* node_lo, float4* node_hi, int2* queue_a, int2* queue_b, float4* nodes4, const float4* __restrict__ tri,
+                   SmallResult* result)
 {
     extern __shared__ float4 sm4[];
     const int n_groups = gpos[n - 1] + ghead[n - 1];
@@ -557,7 +559,7 @@ build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__
     while (n_in > 0) {
         const int2* q_in = (level & 1) ? queue_b : queue_a;
         int2* q_out = (level & 1) ? queue_a : queue_b;
-        for (int k = tid; k < n_in; k += SMALL_THREADS) collapse_entry(q_in[k], children, leaf_lo, leaf_hi, node_lo, node_hi, q_out, s_counters, nodes4);
+        for (int k = tid; k < n_in; k += SMALL_THREADS) collapse_entry(q_in[k], children, leaf_lo, leaf_hi, node_lo, node_hi, q_out, s_counters, nodes4, tri);
         __syncthreads();
         n_in = s_counters[1];
         __syncthreads();
@@ -568,7 +570,7 @@ build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__
     if (tid == 0) {
         double total = 0.0;
         for (int w = 0; w < SMALL_THREADS / 32; w++) total += s_sah[w];
-        result->root = n_inner > 0 ? 0 : ~0;
+        result->root = n_inner > 0 ? 0 : TRT_LEAF_REF(0, n);               // a single run: the root is that leaf
         result->n_wide = n_inner > 0 ? s_counters[0] : 0;
         result->wide_depth = level;
         result->n_groups = n_groups;
@@ -615,7 +617,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     }
     const int n = in.n_tris;
     if (n == 0) return cudaSuccess;
-    if (n > (1 << IDX_BITS)) return cudaErrorInvalidValue;
+    if (n > (1 << TRT_LEAF_POS_BITS)) return cudaErrorInvalidValue;
 
     // ---- scratch layout (the caller owns the buffer: trt_build_scratch_bytes) ------------------------
     size_t cub_bytes = 0, scan_bytes = 0;
@@ -705,7 +707,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
         static bool attr_set = false;
         if (!attr_set) { BT(cudaFuncSetAttribute(build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
         build_small_kernel<<<1, SMALL_THREADS, smem, stream>>>(n, ghead, gpos, gfirst, leaf_lo, leaf_hi, radius, children, node_lo, node_hi,
-                                                                (int2*)(base + o_queue_a), (int2*)(base + o_queue_b), out.nodes, d_res);
+                                                                (int2*)(base + o_queue_a), (int2*)(base + o_queue_b), out.nodes, out.tri, d_res);
         BT(cudaGetLastError());
         int h_small2[64];
         BT(cudaMemcpyAsync(h_small2, small, sizeof h_small2, cudaMemcpyDeviceToHost, stream));
@@ -732,7 +734,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
     scene_scale(h_bounds);
     out.n_groups = n_groups;
     if (n_groups == 1) {
-        out.root = ~0; out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;
+        out.root = TRT_LEAF_REF(0, n); out.max_depth = 1; out.n_wide_nodes = 0; out.wide_depth = 0;       // one run of n <= 16 triangles
     } else {
         int root = 0;
         if (lbvh) {
@@ -789,7 +791,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
         int n_in = 1, level = 0;
         while (n_in > 0) {
             collapse_level<<<(n_in + TB - 1) / TB, TB, 0, stream>>>(children, leaf_lo, leaf_hi, node_lo, node_hi,
-                                                                   q[level & 1], n_in, q[(level + 1) & 1], counters, out.nodes);
+                                                                   q[level & 1], n_in, q[(level + 1) & 1], counters, out.nodes, out.tri);
             BT(cudaGetLastError());
             BT(cudaMemcpyAsync(h_counters, counters, sizeof h_counters, cudaMemcpyDeviceToHost, stream));
             BT(cudaStreamSynchronize(stream));

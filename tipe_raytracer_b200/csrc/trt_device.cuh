@@ -16,6 +16,11 @@
 #define TRT_MAX_SMEM_SPHERES 1024
 #define TRT_STACK_DEPTH 96                    /* traversal stack entries per lane (local memory) */
 #define TRT_CHILD_EMPTY 0x7ffffffe             /* unused child slot of a 4-wide node */
+/* leaf reference = ~(position of the run's first triangle | (run length - 1) << 27): the traversal knows how many records to
+   test without waiting for the first one (run length <= 16, positions < 2^27) */
+#define TRT_LEAF_POS_BITS 27
+#define TRT_LEAF_POS_MASK ((1 << TRT_LEAF_POS_BITS) - 1)
+#define TRT_LEAF_REF(pos, count) (~((pos) | (((count) - 1) << TRT_LEAF_POS_BITS)))
 
 // ---- device scene (all pointers are device pointers owned by the ctx) -----------------------
 struct DevScene {

@@ -213,7 +213,7 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
                                                  int src_leaf, int twin_leaf, bool any_hit, Trav& tr, int* stack, TraceCounters& cnt)
 {
     const bool leaf = tr.node < 0;
-    const int idx = leaf ? ~tr.node : tr.node;
+    const int idx = leaf ? (~tr.node & TRT_LEAF_POS_MASK) : tr.node;              // leaf reference: position | (run length - 1) << 27
     const float4* rec = leaf ? sc.tri + 4 * (size_t)idx : sc.nodes + 8 * (size_t)idx;
     const int rot = leaf ? 0 : (idx & 3);
     float4 f0a, f0b, f1a, f1b, f2a = make_float4(0, 0, 0, 0), f2b = f2a, f3a = f2a, f3b = f2a;
@@ -253,7 +253,7 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
         // a leaf is a RUN of triangles that share one box (bvh_build.cu, group_heads): 64-byte records idx, idx+1, ...;
         // the head record carries the count.  The first record came with the unified fetch above.
         int next = stack[--tr.sp];
-        int left = __float_as_int(f1b.w);
+        int left = ((~tr.node) >> TRT_LEAF_POS_BITS) + 1;
         int p = idx;
         for (;;) {
             if (p != src_leaf && p != twin_leaf) {
@@ -332,7 +332,7 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
     }
     if (tr.node < 0 && pend == 0) {
         pend = tr.node; tr.node = stack[--tr.sp];
-        if (exp_flags & 1) prefetch_l1(sc.tri + 4 * (size_t)(~pend));
+        if (exp_flags & 1) prefetch_l1(sc.tri + 4 * (size_t)(~pend & TRT_LEAF_POS_MASK));
     }
     if ((exp_flags & 2) && tr.node >= 0 && tr.node != TRT_TRAV_DONE) prefetch_l1(sc.nodes + 8 * (size_t)tr.node);
     // the parked leaves are tested once a 1/share part of the lanes that are still inside hold one, or no lane can advance
@@ -342,8 +342,75 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
     const unsigned pend_mask = __ballot_sync(0xffffffffu, pend != 0);
     const unsigned adv_mask = __ballot_sync(0xffffffffu, can_advance);
     if (__popc(pend_mask) * share >= __popc(adv_mask | pend_mask) || (pend_mask != 0 && adv_mask == 0)) {
+#ifdef TRT_COOP_LEAF
+        // WARP-COOPERATIVE leaf tests: the triangles of all parked runs are dealt out to all 32 lanes (prefix sum of the run
+        // lengths; lane w of a pass takes the w-th triangle and fetches the ray of the lane that owns it through shuffles),
+        // tested in one Moller-Trumbore pass, and every owner collects the nearest hit of its own run (first-wins ties by the
+        // caller's index, exactly like the sequential loop) - instead of a loop as long as the longest run at ~6 of 32 lanes.
+        {
+            const int run_n = pend != 0 ? (((~pend) >> TRT_LEAF_POS_BITS) + 1) : 0;
+            const int p0 = ~pend & TRT_LEAF_POS_MASK;
+            int incl = run_n;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, off); if ((int)(threadIdx.x & 31) >= off) incl += y; }
+            const int excl = incl - run_n;
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            const int ns = sc.n_spheres;
+            const int lane_id = threadIdx.x & 31;
+            float best_t = tr.t; int best_orig = -2, best_p = -1; float best_u = 0.0f, best_v = 0.0f;      // -2: the incumbent's caller index is not loaded yet
+            for (int base = 0; base < total; base += 32) {
+                const int w = base + lane_id;
+                int owner = 0;
+#pragma unroll
+                for (int k = 16; k >= 1; k >>= 1) { const int v = __shfl_sync(0xffffffffu, incl, owner + k - 1); if (v <= w) owner += k; }
+                owner = min(owner, 31);
+                const int tri = __shfl_sync(0xffffffffu, p0 - excl, owner) + w;
+                const float3 ro = f3(__shfl_sync(0xffffffffu, o.x, owner), __shfl_sync(0xffffffffu, o.y, owner), __shfl_sync(0xffffffffu, o.z, owner));
+                const float3 rdir = f3(__shfl_sync(0xffffffffu, d.x, owner), __shfl_sync(0xffffffffu, d.y, owner), __shfl_sync(0xffffffffu, d.z, owner));
+                const int sl = __shfl_sync(0xffffffffu, src_leaf, owner), tl = __shfl_sync(0xffffffffu, twin_leaf, owner);
+                float t = __int_as_float(0x7f800000), u = 0.0f, v = 0.0f; int orig = 0x7fffffff;
+                if (w < total && tri != sl && tri != tl) {
+                    const float4* rec = sc.tri + 4 * (size_t)tri;
+                    float4 f0a, f0b, f1a, f1b;
+                    ldg256(rec, f0a, f0b); ldg256(rec + 2, f1a, f1b);
+                    if (COUNT) cnt.tri_tests++;
+                    float tt, uu, vv;
+                    if (triangle_test(f0a, f0b, f1a, ro, rdir, sc.tri_tmin, tt, uu, vv)) { t = tt; u = uu; v = vv; orig = __float_as_int(f1b.x); }
+                }
+                // owners collect from the lanes of their run that fall into this pass
+                const int s0 = max(excl, base) - base, s1 = min(incl, base + 32) - base;
+                const int seg = (pend != 0 && s1 > s0) ? s1 - s0 : 0;
+                const int maxlen = __reduce_max_sync(0xffffffffu, seg);
+                int got = -1;
+                for (int j = 0; j < maxlen; j++) {
+                    const int src = min(max(s0, 0) + j, 31);
+                    const float tj = __shfl_sync(0xffffffffu, t, src);
+                    const int oj = __shfl_sync(0xffffffffu, orig, src);
+                    if (j < seg && tj <= best_t && oj != 0x7fffffff) {
+                        bool take = tj < best_t;
+                        if (!take) {                                 // tie: the lower index in the caller's array wins (main.c:85 strict '<'); a sphere keeps it
+                            if (best_orig == -2) best_orig = tr.prim >= ns ? __ldg(sc.tri_orig + (tr.prim - ns)) : -1;
+                            take = oj < best_orig;
+                        }
+                        if (take) { best_t = tj; best_orig = oj; got = src; }
+                    }
+                }
+                const int gsrc = max(got, 0);
+                const float gu = __shfl_sync(0xffffffffu, u, gsrc), gv = __shfl_sync(0xffffffffu, v, gsrc);
+                if (got >= 0) { best_u = gu; best_v = gv; best_p = p0 + (base + got - excl); }
+            }
+            if (pend != 0) {
+                pend = 0;
+                if (best_p >= 0) {
+                    tr.t = best_t; tr.prim = ns + best_p; tr.u = best_u; tr.v = best_v;
+                    if (any_hit) { tr.node = TRT_TRAV_DONE; tr.sp = 0; }
+                }
+            }
+        }
+#else
         if (pend != 0) {
-            int p = ~pend;
+            int p = ~pend & TRT_LEAF_POS_MASK;
+            const int run_len = ((~pend) >> TRT_LEAF_POS_BITS) + 1;
             pend = 0;
             const float4* rec = sc.tri + 4 * (size_t)p;
             float4 f0a, f0b, f1a, f1b;
@@ -368,7 +435,7 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
             // (the record after the last one of a run is fetched too: the triangle buffer has 256 bytes of slack for that)
             float4 g0a, g0b, g1a, g1b;
             ldg256(rec + 4, g0a, g0b); ldg256(rec + 6, g1a, g1b);
-            int left = __float_as_int(f1b.w);
+            int left = run_len;
             for (;;) {
                 TRT_LEAF_TEST(p, f0a, f0b, f1a, f1b)
                 if (left >= 2) { TRT_LEAF_TEST(p + 1, g0a, g0b, g1a, g1b) }
@@ -379,7 +446,7 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
                 ldg256(rec + 4, g0a, g0b); ldg256(rec + 6, g1a, g1b);
             }
 #else
-            int left = __float_as_int(f1b.w);
+            int left = run_len;
             for (;;) {
                 TRT_LEAF_TEST(p, f0a, f0b, f1a, f1b)
                 if (--left <= 0) break;
@@ -389,6 +456,7 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
 #endif
 #undef TRT_LEAF_TEST
         }
+#endif
     }
 }
 
