@@ -131,6 +131,25 @@ def test_slot_pool_kernel_is_bit_identical_to_the_register_kernel(rt):
     assert a["stats"]["rays"] == b["stats"]["rays"] and c["stats"]["rays"] == d["stats"]["rays"]
 
 
+def test_packet_primaries_are_bit_identical_to_the_register_kernel(rt):
+    """Engine 4: the primary rays of the frame traced as 32-ray packets with one warp-shared stack (primary_packet.cu), the
+    path-tracing kernel starting every path from its stored hit.  Same image, same ray count; ragged size, AO on a mesh too."""
+    for use_ao, width, spp in ((False, 200, 12), (True, 97, 5)):
+        sc = S.nature_mesh(); sc.use_ao = use_ao
+        rt.scene_set(sc)
+        rp = S.params_for(sc, width=width, spp=spp)
+        try:
+            os.environ["TRT_ENGINE"] = "1"
+            a = rt.render(rp)
+            os.environ["TRT_ENGINE"] = "4"
+            b = rt.render(rp)
+        finally:
+            os.environ.pop("TRT_ENGINE", None)
+        for k in ("canva", "albedo", "normal"):
+            assert a[k].tobytes() == b[k].tobytes()
+        assert a["stats"]["rays"] == b["stats"]["rays"] and b["stats"]["kernel_launches"] == a["stats"]["kernel_launches"] + 1
+
+
 def test_in_process_multi_gpu_is_bit_identical():
     import torch
     if torch.cuda.device_count() < 2:

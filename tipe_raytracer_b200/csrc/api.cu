@@ -41,6 +41,7 @@ struct DeviceCtx {
     cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_c = nullptr, ev_d = nullptr;
     // scene: grow-only device buffers, reused by every trt_scene_set (no cudaMalloc/cudaFree churn per frame)
     Buf sph_raw, tri_raw, quel_mat, sph, sph_mat, tri, tri_uv, tri_orig, nodes, texels, mats_raw, ov_raw, scratch, sky;
+    Buf prehit;                                // engine 4: primary hits of the frame, 16 B per path
     DevScene scene{};
     // work buffers
     unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
@@ -389,7 +390,31 @@ int launch_trace(trt_ctx* ctx, DeviceCtx& d, const trt_params* p, int spp, int o
         A.pp_fit32 = (A.n_items + 2 * (long long)A.pool < (1LL << 32)) ? 1 : 0;
         pool_engine = trt_pool_smem_bytes(A) <= (size_t)200 * 1024 / 4;   // 4+ CTAs of 128 threads per SM must fit
     }
-    if (pool_engine) {
+    // engine 4 (opt-in, TRT_ENGINE=4): the primary rays of the frame as packets first (primary_packet.cu), then K2 starts
+    // every path from its stored hit
+    bool packet_engine = false;
+    if (knob("TRT_ENGINE", 0) == 4 && d.scene.n_tris > 0 && !brute && A.defer > 0 && A.top_nodes == 0 && p->nbRebondMax >= 1 && spp < (1 << 26)) {
+        const size_t npix = (size_t)A.W * (size_t)A.H, bytes = npix * (size_t)spp * sizeof(float4);
+        if (bytes <= ((size_t)knob("TRT_TUNE_PREHIT_GB", 8) << 30) && d.prehit.ensure(bytes) == cudaSuccess) {
+            auto magic = [](unsigned d) { unsigned long long m = (1ULL << 32) / d; return (unsigned)(m > 0xffffffffULL ? 0xffffffffULL : m); };
+            RenderArgs K = A;
+            K.pp_per_tile = 32u * (unsigned)spp;
+            K.pp_m_per_tile = magic(K.pp_per_tile); K.pp_m_spp = magic((unsigned)spp);
+            K.n_items = my_tiles * 32 * (long long)spp;
+            K.pp_fit32 = (K.n_items + 64 < (1LL << 32)) ? 1 : 0;
+            K.pool = knob("TRT_TUNE_PK_POOL", 8);                       // packets per reservation
+            K.item_counter = d.ctrs + 15;
+            CU(ctx, cudaEventRecord(d.ev_a, d.stream));
+            CU(ctx, trt_launch_primary_packets(K, d.n_sms, (float4*)d.prehit.p, spp, count_tests, d.stream));
+            A.prehit = (const float4*)d.prehit.p; A.prehit_slab = spp;
+            packet_engine = true;
+        } else cudaGetLastError();
+    }
+    if (packet_engine) {
+        CU(ctx, trt_launch_pathtrace(A, d.n_sms, blocks_per_sm, brute, count_tests, d.stream));
+        CU(ctx, cudaEventRecord(d.ev_b, d.stream));
+        d.last_launches = 2;
+    } else if (pool_engine) {
         CU(ctx, cudaEventRecord(d.ev_a, d.stream));
         CU(ctx, trt_launch_pathtrace_pool(A, d.n_sms, blocks_per_sm, count_tests, d.stream));
         CU(ctx, cudaEventRecord(d.ev_b, d.stream));
@@ -534,6 +559,7 @@ TRT_API void trt_destroy(trt_ctx* ctx)
         if (d.stream) cudaStreamSynchronize(d.stream);
         free_scene(d);
         d.sky.release();
+        d.prehit.release();
         if (d.accum) cudaFree(d.accum);
         if (d.out) cudaFree(d.out);
         if (d.h_stage) cudaFreeHost(d.h_stage);

@@ -32,7 +32,7 @@
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER, bool TOP = false>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER, bool TOP = false, bool PREHIT = false>
 __global__ void __launch_bounds__(PT_THREADS, HAS_TRIS ? PT_MIN_BLOCKS_MESH : PT_MIN_BLOCKS)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
@@ -196,7 +196,12 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
         // ---- A4. new rays: sphere scan, scene-box cull, traversal set-up ---------------------------
         if (new_ray) {
             const bool ao_ray = (phase == PH_AO);
-            if (!HAS_TRIS && fuse_ao) {
+            if (PREHIT && P.bounce == 0 && !ao_ray) {
+                // a fresh path: its primary ray was traced by the packet kernel (primary_packet.cu), and counted there
+                const float4 h = __ldg(A.prehit + (size_t)pixel * (size_t)A.prehit_slab + (size_t)s_cur);
+                tr.t = h.x; tr.prim = __float_as_int(h.y); tr.u = h.z; tr.v = h.w;
+                tr.node = TRT_TRAV_DONE; tr.sp = 0;
+            } else if (!HAS_TRIS && fuse_ao) {
                 const bool do_bounce = !ao_ray, do_ao = ao_ray || P.ao_pending;
                 bool occluded;
                 spheres_pair<COUNT>(sc, s_sph, P.o, P.d, P.d_ao, do_bounce, do_ao, P.src_prim, tr, occluded, cnt);
@@ -366,7 +371,7 @@ cudaError_t trt_launch_primary_fp32(const RenderArgs& A, int* id, float* t, cuda
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false, bool TOP = false>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false, bool TOP = false, bool PREHIT = false>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
 {
     {
@@ -377,14 +382,14 @@ static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cu
         const char* v = getenv("TRT_TUNE_CARVEOUT");
         if (v && *v) pct = atoi(v);
         if (pct > 100) pct = 100;
-        cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         // more than ~460 spheres: the sphere table + the per-lane sums pass the 48 KB a kernel gets without asking
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
     }
-    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP><<<grid, PT_THREADS, smem, stream>>>(A);
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 
@@ -399,6 +404,8 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
     if (top) return launch_variant<true, false, false, true, true>(A, grid, smem, stream);
+    if (A.prehit && A.defer > 0) return count_tests ? launch_variant<true, false, true, true, false, true>(A, grid, smem, stream)
+                                                     : launch_variant<true, false, false, true, false, true>(A, grid, smem, stream);
     if (A.defer > 0) return count_tests ? launch_variant<true, false, true, true>(A, grid, smem, stream)
                                         : launch_variant<true, false, false, true>(A, grid, smem, stream);
     return count_tests ? launch_variant<true, false, true>(A, grid, smem, stream)

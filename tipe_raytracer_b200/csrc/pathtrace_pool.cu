@@ -36,28 +36,6 @@ __device__ __forceinline__ unsigned long long pp_globaltimer()
     return t;
 }
 
-// path index -> (pixel of an 8x4 tile, sample).  Paths are numbered sample-fastest, then the 32 pixels of a tile, then tiles.
-__device__ __forceinline__ void decode_path(const RenderArgs& A, long long g, int& px, int& py, int& sample)
-{
-    int p, tile;
-    if (A.pp_fit32) {
-        unsigned rem, s, x;
-        unsigned t = fastdiv((unsigned)g, A.pp_per_tile, A.pp_m_per_tile, rem);
-        p = (int)fastdiv(rem, (unsigned)A.spp, A.pp_m_spp, s);
-        sample = (int)s;
-        t = t * (unsigned)A.tile_stride + (unsigned)A.tile_offset;
-        const int ty = (int)fastdiv(t, (unsigned)A.tiles_x, A.m_tiles_x, x);
-        px = (int)x * 8 + (p & 7); py = ty * 4 + (p >> 3);
-        return;
-    }
-    const long long per_tile = 32LL * A.spp;
-    const long long tl = g / per_tile;
-    const long long rem = g - tl * per_tile;
-    p = (int)(rem / A.spp); sample = (int)(rem - (long long)p * A.spp);
-    tile = (int)(tl * A.tile_stride + A.tile_offset);
-    px = (tile % A.tiles_x) * 8 + (p & 7); py = (tile / A.tiles_x) * 4 + (p >> 3);
-}
-
 // Slot record, 6 (7 with ambient occlusion) float4 per slot, stored as q[quad][slot]:
 //   q0 (ray origin, hit distance)              q1 (direction of the ray to trace, bits: hit primitive)
 //   q2 bits(src_prim, src_twin, any-hit, pixel) q3 (rayColor T, current refractive index)

@@ -34,6 +34,8 @@ struct RenderArgs {
     int defer;                          // megakernel: > 0 = deferred leaves, tested once 1/defer of the lanes inside hold one (bvh_trip_deferred)
     int item_order;                     // see decode_item (trt_shade.cuh)
     int top_nodes;                      // megakernel: this many wide nodes (the top levels) are staged into shared memory by TMA; 0 = off (TRT_TUNE_TOPK)
+    // engine 4: the primary rays were traced as packets (primary_packet.cu); prehit[pixel * prehit_slab + sample] = (t, bits(prim), u, v)
+    const float4* prehit; int prehit_slab;
     int exp_flags;                      // experiments (TRT_TUNE_EXP): 1 = L1 prefetch of a leaf's triangles when it is parked, 2 = of the next node after a visit
     // slot-pool kernel (pathtrace_pool.cu): n_items = paths of this launch, pool = paths a warp reserves per atomic
     int pp_slots;                       // path slots per warp (<= 64)
@@ -59,6 +61,8 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
 // slot-pool kernel for triangle meshes (pathtrace_pool.cu); blocks_per_sm 0 = default
 cudaError_t trt_launch_pathtrace_pool(const RenderArgs& A, int n_sms, int blocks_per_sm, bool count_tests, cudaStream_t stream);
 size_t trt_pool_smem_bytes(const RenderArgs& A);
+// packet traversal of the primary rays into hits[pixel * slab + sample] (primary_packet.cu)
+cudaError_t trt_launch_primary_packets(const RenderArgs& A, int n_sms, float4* hits, int slab, bool count_tests, cudaStream_t stream);
 cudaError_t trt_launch_primary_fp32(const RenderArgs& A, int* id, float* t, cudaStream_t stream);     // K2's FP32 first hit, pixel centres
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream);
 cudaError_t trt_launch_resolve_hdr(int npix, int divisor, const long long* acc, float* radiance, float* albedo, float* normal, int n_sms, cudaStream_t stream);

@@ -63,6 +63,28 @@ __device__ __forceinline__ void decode_item(const RenderArgs& A, long long item,
     tx = tile % A.tiles_x; ty = tile / A.tiles_x;
 }
 
+// path index -> (pixel of an 8x4 tile, sample).  Paths are numbered sample-fastest, then the 32 pixels of a tile, then tiles.
+__device__ __forceinline__ void decode_path(const RenderArgs& A, long long g, int& px, int& py, int& sample)
+{
+    int p, tile;
+    if (A.pp_fit32) {
+        unsigned rem, s, x;
+        unsigned t = fastdiv((unsigned)g, A.pp_per_tile, A.pp_m_per_tile, rem);
+        p = (int)fastdiv(rem, (unsigned)A.spp, A.pp_m_spp, s);
+        sample = (int)s;
+        t = t * (unsigned)A.tile_stride + (unsigned)A.tile_offset;
+        const int ty = (int)fastdiv(t, (unsigned)A.tiles_x, A.m_tiles_x, x);
+        px = (int)x * 8 + (p & 7); py = ty * 4 + (p >> 3);
+        return;
+    }
+    const long long per_tile = 32LL * A.spp;
+    const long long tl = g / per_tile;
+    const long long rem = g - tl * per_tile;
+    p = (int)(rem / A.spp); sample = (int)(rem - (long long)p * A.spp);
+    tile = (int)(tl * A.tile_stride + A.tile_offset);
+    px = (tile % A.tiles_x) * 8 + (p & 7); py = (tile / A.tiles_x) * 4 + (p >> 3);
+}
+
 // fill_canva's per-sample set-up (main.c:265-271) + get_ray (camera.h:42-54): the primary ray of (pixel, sample).
 // A.cam_corner = coin_bas_gauche - origin, formed in FP64 on the host.
 __device__ __forceinline__ void camera_ray(const RenderArgs& A, int pixel, int px, int py, int sample, float3& o, float3& d)
