@@ -339,7 +339,7 @@ def main():
     # ---- e2e: the C-ABI call a user makes, host buffers, H2D + D2H inside the timed region --------
     host = dict(canva=np.empty((npix, 3)), albedo=np.empty((npix, 3)), normal=np.empty((npix, 3)))
     h2d = int(sc.spheres.nbytes + sc.triangles.nbytes + sc.mat_list.nbytes + sc.quel_mat_pour_tri.nbytes)
-    d2h = 3 * npix * 24
+    d2h = 3 * npix + 2 * npix * 24          # canva crosses PCIe as 3 bytes per pixel (widened to doubles on the host), the two AOV tables as doubles
     e2e_parts = {"scene_set_ms": 0.0}
     rp_job = S.params_for(sc, spp=spp * world)                # the N*spp-sample frame; every rank takes its N-th of the samples
 
