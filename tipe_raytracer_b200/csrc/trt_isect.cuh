@@ -165,6 +165,8 @@ __device__ __forceinline__ void spheres_pair(const DevScene& sc, const float4* _
     const float a = dot3(d, d), inv_a = __frcp_rn(a);
     const float a2 = dot3(d_ao, d_ao), eps2 = 1e-4f * a2;
     const int ns = sc.n_spheres;
+    // unrolled by 5 (same-call A/B: C1 11.45 -> 11.07 ms, C5 -3.6 %; by 2: no change, by 10: 11.26)
+#pragma unroll 5
     for (int k = 0; k < ns; k++) {
         const float4 cr = s_sph[k];
         const float3 oc = f3(o.x - cr.x, o.y - cr.y, o.z - cr.z);
