@@ -451,6 +451,10 @@ int check_watchdog(trt_ctx* ctx)
 {
     for (auto& d : ctx->devs)
         if (d.h_ctrs[14] != 0) return fail(ctx, TRT_ERR_CUDA, "path-tracing kernel gave up after 20 s on device %d (scheduler watchdog)", d.dev);
+#ifdef TRT_DEBUG_BOUNDS
+    for (auto& d : ctx->devs)
+        if (d.h_ctrs[13] != 0) return fail(ctx, TRT_ERR_CUDA, "TRT_DEBUG_BOUNDS: index out of range on device %d, check %llu (trt_isect.cuh / pathtrace*.cu)", d.dev, (unsigned long long)d.h_ctrs[13]);
+#endif
     return TRT_OK;
 }
 
@@ -680,7 +684,7 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
         s.sky = sky; s.sky_w = sky_w; s.sky_h = sky_h;
         s.n_spheres = nbSpheres; s.sph = bo.sph; s.sph_mat = bo.sph_mat; s.sph64 = (const double*)d.sph_raw.p;
         s.n_tris = nbTriangles; s.tri = bo.tri; s.tri_uv = bo.tri_uv; s.tri_orig = bo.tri_orig; s.tri64 = (const double*)d.tri_raw.p;
-        s.quel_mat = (const int*)d.quel_mat.p; s.nodes = bo.nodes; s.root = bo.root;
+        s.quel_mat = (const int*)d.quel_mat.p; s.nodes = bo.nodes; s.root = bo.root; s.n_nodes = bo.n_wide_nodes;
         s.texels = bo.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
         s.tri_tmin = bo.tri_tmin;
         s.root_lo = bo.root_lo; s.root_hi = bo.root_hi;

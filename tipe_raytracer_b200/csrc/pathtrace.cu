@@ -65,6 +65,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
     for (int c = 0; c < 9; c++) s_acc[c * PT_THREADS + threadIdx.x] = 0;
     __syncthreads();
 
+    TRT_DEBUG_INIT(A);
     const DevScene& sc = A.scene;
     const int lane = threadIdx.x & 31;
     const int W = A.W, H = A.H;

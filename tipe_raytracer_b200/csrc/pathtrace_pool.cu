@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(PP_THREADS, MIN_BLOCKS)
 pathtrace_pool_kernel(const __grid_constant__ RenderArgs A)
 {
     extern __shared__ float4 smem[];
+    TRT_DEBUG_INIT(A);
     const DevScene& sc = A.scene;
     const int ns = sc.n_spheres;
     float4* s_sph = smem;                                   // [n_spheres]
@@ -123,6 +124,7 @@ pathtrace_pool_kernel(const __grid_constant__ RenderArgs A)
                 const int n = min(32, hr_count);
                 const bool mine = lane < n;
                 const int s = mine ? (int)hr_ring[(hr_head + lane) & (PP_RING - 1)] : 0;
+                TRT_CHECK(s >= 0 && s < N && hr_count >= 0 && rr_count >= 0 && hr_count + rr_count <= N, 201);
                 hr_head = (hr_head + n) & (PP_RING - 1); hr_count -= n;
 
                 PathState P;
@@ -265,6 +267,7 @@ pathtrace_pool_kernel(const __grid_constant__ RenderArgs A)
                     const int rank = __popc(need_mask & lanemask_lt());
                     if (slot < 0 && rank < rr_count) {
                         slot = (int)rr_ring[(rr_head + rank) & (PP_RING - 1)];
+                        TRT_CHECK(slot >= 0 && slot < N, 202);
                         PP_LOAD_RAY(slot)
                         const float4 q0 = wq[slot], q1 = wq[N + slot];
                         tr.t = q0.w; tr.prim = __float_as_int(q1.w); tr.u = tr.v = 0.0f;

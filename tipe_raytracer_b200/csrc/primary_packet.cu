@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(PK_THREADS, 4)
 primary_packet_kernel(const __grid_constant__ RenderArgs A, float4* __restrict__ hits, int slab)
 {
     extern __shared__ float4 smem[];
+    TRT_DEBUG_INIT(A);
     const DevScene& sc = A.scene;
     const int ns = sc.n_spheres;
     float4* s_sph = smem;                                                        // [n_spheres]
@@ -62,6 +63,7 @@ primary_packet_kernel(const __grid_constant__ RenderArgs A, float4* __restrict__
                 int sp = 0;                                                     // warp-uniform
                 int node = sc.root;
                 for (;;) {
+                    TRT_CHECK(sp >= 0 && sp + 3 <= PK_STACK && (node < 0 || node < sc.n_nodes), 301);
                     if (node >= 0) {
                         // ---- inner node: uniform fetch, four slab tests per lane ---------------------------------
                         const float4* rec = sc.nodes + 8 * (size_t)node;
@@ -108,6 +110,7 @@ primary_packet_kernel(const __grid_constant__ RenderArgs A, float4* __restrict__
                         // ---- leaf: the run's triangles, uniform fetches, every lane tests its own ray -----------------
                         int p = ~node & TRT_LEAF_POS_MASK;
                         const int run_len = ((~node) >> TRT_LEAF_POS_BITS) + 1;
+                        TRT_CHECK(p >= 0 && p + run_len <= sc.n_tris, 302);
                         for (int k = 0; k < run_len; k++, p++) {
                             const float4* rec = sc.tri + 4 * (size_t)p;
                             float4 f0a, f0b, f1a, f1b;

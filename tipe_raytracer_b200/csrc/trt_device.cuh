@@ -31,6 +31,7 @@ struct DevScene {
     const double* sph64;        // [14n] raw copy of the caller's sphere array (112 B each) for the FP64 primary pass
     // triangles, stored in BVH leaf order
     int n_tris;
+    int n_nodes;                // wide nodes of the BVH (range checks of -DTRT_DEBUG_BOUNDS builds)
     const float4* tri;          // [4n]  64 B: (A.xyz, AB.x) (AB.yz, AC.xy) (AC.z, N.xyz) (caller index, twin leaf, ordinal, -), N = AB x AC un-normalised
     const float4* tri_uv;       // [2n]  (uvA, uvB) (uvC, bits(material ordinal), bits(twin leaf position or -1))
     const int*    tri_orig;     // [n]   leaf position -> index in the caller's triangle array
@@ -53,6 +54,17 @@ struct DevScene {
 };
 // material record (sphere or texel), 3 x float4:
 //   [0] diffuse.rgb, alpha   [1] emission.rgb, emissionStrength   [2] reflectionStrength, materialIndex, 0, 0
+
+// ---- -DTRT_DEBUG_BOUNDS: range checks of every index the kernels form (compute-sanitizer stand-in) -----------------------
+// A violation sets *trt_debug_flag (counters[12]; the render call then fails with the code) and the access is skipped / clamped.
+#ifdef TRT_DEBUG_BOUNDS
+static __device__ unsigned long long* trt_debug_flag_ptr;      // one per translation unit; every kernel sets it on entry (TRT_DEBUG_INIT)
+#define TRT_DEBUG_INIT(A) do { if (threadIdx.x == 0) trt_debug_flag_ptr = (A).counters + 12; __syncthreads(); } while (0)
+#define TRT_CHECK(cond, code) do { if (!(cond)) { if (trt_debug_flag_ptr) atomicMax(trt_debug_flag_ptr, (unsigned long long)(code)); } } while (0)
+#else
+#define TRT_CHECK(cond, code) do { } while (0)
+#define TRT_DEBUG_INIT(A) do { } while (0)
+#endif
 
 // ---- float3 helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }

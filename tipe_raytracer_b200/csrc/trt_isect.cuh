@@ -216,6 +216,8 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
 {
     const bool leaf = tr.node < 0;
     const int idx = leaf ? (~tr.node & TRT_LEAF_POS_MASK) : tr.node;              // leaf reference: position | (run length - 1) << 27
+    TRT_CHECK(leaf ? (idx + ((~tr.node) >> TRT_LEAF_POS_BITS) < sc.n_tris) : (idx < sc.n_nodes), 104);
+    TRT_CHECK(tr.sp >= 1 && tr.sp + 3 <= TRT_STACK_DEPTH, 105);
     const float4* rec = leaf ? sc.tri + 4 * (size_t)idx : sc.nodes + 8 * (size_t)idx;
     const int rot = leaf ? 0 : (idx & 3);
     float4 f0a, f0b, f1a, f1b, f2a = make_float4(0, 0, 0, 0), f2b = f2a, f3a = f2a, f3b = f2a;
@@ -293,6 +295,8 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
                                                   const float4* s_top = nullptr, int top_k = 0)
 {
     if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) {
+        TRT_CHECK(tr.node < sc.n_nodes, 101);
+        TRT_CHECK(tr.sp >= 1 && tr.sp + 3 <= TRT_STACK_DEPTH, 102);
         const int rot = tr.node & 3;
         float4 f0a, f0b, f1a, f1b, f2a, f2b, f3a, f3b;
         if (TOP && tr.node < top_k) {
@@ -413,6 +417,7 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
         if (pend != 0) {
             int p = ~pend & TRT_LEAF_POS_MASK;
             const int run_len = ((~pend) >> TRT_LEAF_POS_BITS) + 1;
+            TRT_CHECK(p >= 0 && p + run_len <= sc.n_tris && run_len <= 16, 103);
             pend = 0;
             const float4* rec = sc.tri + 4 * (size_t)p;
             float4 f0a, f0b, f1a, f1b;
@@ -494,6 +499,7 @@ __device__ __forceinline__ Material triangle_material(const DevScene& sc, int le
     const int y = min((int)(tv * (float)sc.tex_h), sc.tex_h - 1);
     const int ordinal = __float_as_int(q1.z);
     twin_out = __float_as_int(q1.w);
+    TRT_CHECK(leaf_pos >= 0 && leaf_pos < sc.n_tris && ordinal >= 0 && ordinal < sc.n_materials && x >= 0 && y >= 0, 106);
     const size_t texel = (size_t)(y * sc.tex_w + x) + (size_t)sc.tex_h * (size_t)sc.tex_w * (size_t)ordinal;
     const float4* rec = sc.texels + 3 * texel;
     return unpack_material(__ldg(rec), __ldg(rec + 1), __ldg(rec + 2));
