@@ -365,6 +365,19 @@ __global__ void ploc_init(int n_groups, const int* __restrict__ gfirst, const fl
     cid[g] = ~p; clo[g] = leaf_lo[p]; chi[g] = leaf_hi[p];
 }
 
+// the same with the group count read on the device (small scenes: the host does not know it yet); d_cnt[0] = clusters, node counter = 0
+__global__ void ploc_init_dev(int n, const int* __restrict__ ghead, const int* __restrict__ gpos, const int* __restrict__ gfirst,
+                              const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int* cid, float4* clo, float4* chi,
+                              int* d_cnt, int* node_counter)
+{
+    const int n_groups = gpos[n - 1] + ghead[n - 1];
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g == 0) { d_cnt[0] = n_groups; d_cnt[1] = n_groups; *node_counter = 0; }
+    if (g >= n_groups) return;
+    const int p = gfirst[g];
+    cid[g] = ~p; clo[g] = leaf_lo[p]; chi[g] = leaf_hi[p];
+}
+
 __global__ void sah_cost_kernel(int n, const int2* __restrict__ children, const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi,
                                 const float4* __restrict__ node_lo, const float4* __restrict__ node_hi, int root, double* sah)
 {
@@ -450,14 +463,16 @@ constexpr int SMALL_THREADS = 1024;
 struct SmallResult { int root, n_wide, wide_depth, n_groups; double sah; };
 
 __global__ void __launch_bounds__(SMALL_THREADS, 1)
-build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__ gpos, const int* __restrict__ gfirst,
+build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__ gpos,
+                   const int* g_cid, const float4* g_clo, const float4* g_chi, const int* d_count, const int* node_counter,
                    const float4* __restrict__ leaf_lo, const float4* __restrict__ leaf_hi, int radius,
                    int2* children, float4* node_lo, float4* node_hi, int2* queue_a, int2* queue_b, float4* nodes4, const float4* __restrict__ tri,
                    SmallResult* result)
 {
     extern __shared__ float4 sm4[];
     const int n_groups = gpos[n - 1] + ghead[n - 1];
-    if (n_groups > SMALL_MAX_GROUPS) { if (threadIdx.x == 0) result->n_groups = n_groups; return; }     // host falls back to the multi-kernel path
+    const int c0 = *d_count;                                // clusters left by the multi-block passes that ran before this kernel
+    if (c0 > SMALL_MAX_GROUPS) { if (threadIdx.x == 0) result->n_groups = -c0; return; }     // host falls back to the multi-kernel path
     float4* clo = sm4;                                      // [SMALL_MAX_GROUPS] cluster boxes, in Morton order
     float4* chi = clo + SMALL_MAX_GROUPS;
     int* cid = (int*)(chi + SMALL_MAX_GROUPS);              // leaf ~p or internal node
@@ -467,12 +482,12 @@ build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__
     __shared__ double s_sah[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int g = tid; g < n_groups; g += SMALL_THREADS) { const int p = gfirst[g]; cid[g] = ~p; clo[g] = leaf_lo[p]; chi[g] = leaf_hi[p]; }
-    if (tid == 0) { s_count = n_groups; s_nodes = 0; }
+    for (int g = tid; g < c0; g += SMALL_THREADS) { cid[g] = g_cid[g]; clo[g] = g_clo[g]; chi[g] = g_chi[g]; }
+    if (tid == 0) { s_count = c0; s_nodes = *node_counter; }
     __syncthreads();
     int root = ~0;
     if (n_groups > 1) {
-        int c = n_groups;
+        int c = c0;
         while (c > 1) {
             // nearest neighbour within the search radius (ties: lowest index)
             for (int i = tid; i < c; i += SMALL_THREADS) {
@@ -706,8 +721,31 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
         const size_t smem = (size_t)SMALL_MAX_GROUPS * (2 * sizeof(float4) + 2 * sizeof(int));
         static bool attr_set = false;
         if (!attr_set) { BT(cudaFuncSetAttribute(build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
-        build_small_kernel<<<1, SMALL_THREADS, smem, stream>>>(n, ghead, gpos, gfirst, leaf_lo, leaf_hi, radius, children, node_lo, node_hi,
-                                                                (int2*)(base + o_queue_a), (int2*)(base + o_queue_b), out.nodes, out.tri, d_res);
+        // optionally (TRT_TUNE_SMALL_PRE) the first passes, while there are thousands of clusters, run on the whole GPU (the neighbour
+        // search of one pass over 2 035 clusters is 260 k box unions: 87 % of the single-CTA kernel's instructions); the tail of the loop,
+        // the SAH report and the collapse run in one CTA.  Nothing comes back to the host in between: grids are sized for n, the count
+        // lives on the device.
+        int* cidp[2] = {(int*)(base + o_queue_a), (int*)(base + o_queue_b)};
+        int* nn = cidp[0] + n; int* flag = cidp[1] + n; int* pos = parent_node;
+        float4* clop[2] = {box_lo, (float4*)(base + o_c1lo)};
+        float4* chip[2] = {box_hi, (float4*)(base + o_c1hi)};
+        int* node_counter = small + 26;
+        int* d_cnt = small + 28;
+        ploc_init_dev<<<grid_n, TB, 0, stream>>>(n, ghead, gpos, gfirst, leaf_lo, leaf_hi, cidp[0], clop[0], chip[0], d_cnt, node_counter);
+        const char* pre_env = getenv("TRT_TUNE_SMALL_PRE");
+        const int pre = pre_env && *pre_env ? atoi(pre_env) : 0;         // measured on C2: 0 / 4 / 6 / 8 passes -> trt_scene_set 0.75 / 0.75 / 0.78 / 0.79 ms: the launches cost what the kernel saves
+        int cur = 0;
+        for (int pass = 0; pass < pre; pass++) {
+            const int* d_c = d_cnt + (pass & 1); int* d_c_next = d_cnt + ((pass + 1) & 1);
+            ploc_nearest<<<grid_n, TB, 0, stream>>>(d_c, clop[cur], chip[cur], radius, nn);
+            ploc_merge<<<grid_n, TB, 0, stream>>>(d_c, n, cidp[cur], clop[cur], chip[cur], nn, node_counter, children, node_lo, node_hi, flag);
+            { size_t tmp = cub_bytes; BT(cub::DeviceScan::ExclusiveSum(base + o_cub, tmp, flag, pos, n, stream)); }
+            ploc_compact<<<grid_n, TB, 0, stream>>>(d_c, d_c_next, cidp[cur], clop[cur], chip[cur], flag, pos, cidp[cur ^ 1], clop[cur ^ 1], chip[cur ^ 1]);
+            cur ^= 1;
+        }
+        build_small_kernel<<<1, SMALL_THREADS, smem, stream>>>(n, ghead, gpos, cidp[cur], clop[cur], chip[cur], d_cnt + (pre & 1), node_counter,
+                                                                leaf_lo, leaf_hi, radius, children, node_lo, node_hi,
+                                                                (int2*)(base + o_queue_a), (int2*)(base + o_queue_b), out.nodes, out.tri, d_res);      // the cluster arrays in the queues' memory are dead once the kernel has loaded them
         BT(cudaGetLastError());
         int h_small2[64];
         BT(cudaMemcpyAsync(h_small2, small, sizeof h_small2, cudaMemcpyDeviceToHost, stream));
