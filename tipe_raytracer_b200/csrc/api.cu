@@ -4,6 +4,8 @@
 // Host logic only; every kernel lives in pathtrace.cu / primary.cu / bvh_build.cu / kat.cu.
 // There is no CPU rendering path in this library: no device => trt_init fails.
 #include <chrono>
+#include <new>
+#include <exception>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -200,9 +202,14 @@ int copy_out(trt_ctx* ctx, DeviceCtx& d, size_t npix, trt_vec3* canva, trt_vec3*
         }
     };
     std::thread th[15];
-    for (int t = 1; t < n_threads; t++) th[t - 1] = std::thread(worker, t);
+    int started = 1;
+    try {
+        for (int t = 1; t < n_threads; t++) { th[t - 1] = std::thread(worker, t); started = t + 1; }
+    } catch (...) {                                     // thread creation failed: never let an exception cross the C ABI; the missing shares are done here
+    }
     worker(0);
-    for (int t = 1; t < n_threads; t++) th[t - 1].join();
+    for (int t = 1; t < started; t++) th[t - 1].join();
+    for (int t = started; t < n_threads; t++) worker(t);
     for (int t = 0; t < n_threads; t++) CU(ctx, errs[t]);
     CU(ctx, cudaStreamSynchronize(d.stream));
     return TRT_OK;
@@ -247,9 +254,14 @@ int staged_upload(trt_ctx* ctx, char* dst, const char* src, size_t n, size_t in_
         }
     };
     std::thread th[7];
-    for (int t = 1; t < n_threads; t++) th[t - 1] = std::thread(worker, t);
+    int started = 1;
+    try {
+        for (int t = 1; t < n_threads; t++) { th[t - 1] = std::thread(worker, t); started = t + 1; }
+    } catch (...) {                                     // no more threads to be had: the ones that started finish, the rest of the chunks are done here
+    }
     worker(0);
-    for (int t = 1; t < n_threads; t++) th[t - 1].join();
+    for (int t = 1; t < started; t++) th[t - 1].join();
+    for (int t = started; t < n_threads; t++) worker(t);
     for (int t = 0; t < n_threads; t++) CU(ctx, errs[t]);
     CU(ctx, cudaEventRecord(r.done, r.stream));
     CU(ctx, cudaStreamWaitEvent(d.stream, r.done, 0));
@@ -466,6 +478,14 @@ double now_ms()
 
 }  // namespace
 
+// No C++ exception may cross the C ABI (std::bad_alloc from a host vector, std::system_error from a thread): the entry points
+// that allocate on the host run their body through this guard.
+#define TRT_GUARDED(ctx, expr)                                                                       \
+    try { return (expr); }                                                                           \
+    catch (const std::bad_alloc&) { return fail(ctx, TRT_ERR_OOM, "out of host memory"); }           \
+    catch (const std::exception& e) { return fail(ctx, TRT_ERR_INVALID, "internal error: %s", e.what()); } \
+    catch (...) { return fail(ctx, TRT_ERR_INVALID, "internal error"); }
+
 // error plumbing for the other translation units of the library (nccl_glue.cu)
 int trt_set_error(trt_ctx* ctx, int code, const char* text) { return fail(ctx, code, "%s", text ? text : ""); }
 
@@ -502,7 +522,8 @@ TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
         return fail(nullptr, TRT_ERR_NO_DEVICE, "no CUDA device (%s); libtipe_rt has no CPU fallback", cudaGetErrorString(e));
     if (n_devices < 1) n_devices = 1;
     if (n_devices > TRT_MAX_RESOLVE_SOURCES) return fail(nullptr, TRT_ERR_INVALID, "at most %d devices", TRT_MAX_RESOLVE_SOURCES);
-    trt_ctx* ctx = new trt_ctx();
+    trt_ctx* ctx = new (std::nothrow) trt_ctx();
+    if (!ctx) return fail(nullptr, TRT_ERR_OOM, "out of host memory");
     for (int k = 0; k < n_devices; k++) {
         DeviceCtx d;
         d.dev = device_ids ? device_ids[k] : k;
@@ -586,7 +607,7 @@ TRT_API int trt_synchronize(trt_ctx* ctx)
     return TRT_OK;
 }
 
-TRT_API int trt_scene_set(trt_ctx* ctx,
+static int trt_scene_set_impl(trt_ctx* ctx,
                           const trt_sphere* sphere_list, int nbSpheres,
                           const trt_triangle* triangle_list, int nbTriangles,
                           const trt_material* mat_list, int tex_width, int tex_height, int nbMaterials,
@@ -728,7 +749,7 @@ TRT_API int trt_scene_set(trt_ctx* ctx,
     return TRT_OK;
 }
 
-TRT_API int trt_sky_set(trt_ctx* ctx, const trt_material* sky_mat_list, int sky_width, int sky_height)
+static int trt_sky_set_impl(trt_ctx* ctx, const trt_material* sky_mat_list, int sky_width, int sky_height)
 {
     if (!ctx) return TRT_ERR_INVALID;
     if (sky_mat_list && (sky_width < 1 || sky_height < 1 || (long long)sky_width * sky_height > (1LL << 30)))
@@ -819,7 +840,7 @@ TRT_API int trt_resolve_device(trt_ctx* ctx, const trt_params* params, const int
     return TRT_OK;
 }
 
-TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+static int trt_resolve_impl(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
                         trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab)
 {
     int rc = check_params(ctx, params);
@@ -871,7 +892,7 @@ TRT_API int trt_resolve_hdr(trt_ctx* ctx, const trt_params* params, const int64_
     return TRT_OK;
 }
 
-TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
+static int trt_render_impl(trt_ctx* ctx, const trt_params* params,
                        trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
 {
     int rc = check_params(ctx, params);
@@ -936,7 +957,7 @@ TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
 }
 
 // One process per GPU (nccl_glue.cu): this rank's share of the samples (or tiles), NCCL reduce onto rank 0, rank 0 resolves.
-TRT_API int trt_render_distributed(trt_ctx* ctx, const trt_params* params, void* nccl_comm, int rank, int n_ranks,
+static int trt_render_distributed_impl(trt_ctx* ctx, const trt_params* params, void* nccl_comm, int rank, int n_ranks,
                                    trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
 {
     int rc = check_params(ctx, params);
@@ -1042,6 +1063,40 @@ TRT_API int trt_primary_fp32(trt_ctx* ctx, const trt_params* params, float* t, i
     cudaFree(d_id);
     CU(ctx, e);
     return TRT_OK;
+}
+
+// ---- guarded entry points (bodies above, *_impl) ----------------------------------------------------------
+TRT_API int trt_scene_set(trt_ctx* ctx,
+                          const trt_sphere* sphere_list, int nbSpheres,
+                          const trt_triangle* triangle_list, int nbTriangles,
+                          const trt_material* mat_list, int tex_width, int tex_height, int nbMaterials,
+                          const int* quelMatPourTri,
+                          const trt_mat_override* overrides, int n_overrides)
+{
+    TRT_GUARDED(ctx, trt_scene_set_impl(ctx, sphere_list, nbSpheres, triangle_list, nbTriangles, mat_list, tex_width, tex_height, nbMaterials, quelMatPourTri, overrides, n_overrides))
+}
+
+TRT_API int trt_sky_set(trt_ctx* ctx, const trt_material* sky_mat_list, int sky_width, int sky_height)
+{
+    TRT_GUARDED(ctx, trt_sky_set_impl(ctx, sky_mat_list, sky_width, sky_height))
+}
+
+TRT_API int trt_render(trt_ctx* ctx, const trt_params* params,
+                       trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
+{
+    TRT_GUARDED(ctx, trt_render_impl(ctx, params, canva, albedo_tab, normal_tab, stats))
+}
+
+TRT_API int trt_resolve(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
+                        trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab)
+{
+    TRT_GUARDED(ctx, trt_resolve_impl(ctx, params, d_accum, canva, albedo_tab, normal_tab))
+}
+
+TRT_API int trt_render_distributed(trt_ctx* ctx, const trt_params* params, void* nccl_comm, int rank, int n_ranks,
+                                   trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats)
+{
+    TRT_GUARDED(ctx, trt_render_distributed_impl(ctx, params, nccl_comm, rank, n_ranks, canva, albedo_tab, normal_tab, stats))
 }
 
 // ---- known-answer entry points ---------------------------------------------------------------------

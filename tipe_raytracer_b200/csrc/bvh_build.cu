@@ -719,8 +719,7 @@ cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream
         const int radius = rad && *rad ? atoi(rad) : 64;
         SmallResult* d_res = (SmallResult*)(small + 32);
         const size_t smem = (size_t)SMALL_MAX_GROUPS * (2 * sizeof(float4) + 2 * sizeof(int));
-        static bool attr_set = false;
-        if (!attr_set) { BT(cudaFuncSetAttribute(build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+        BT(cudaFuncSetAttribute(build_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      // per device: set on every call (cheap), not once per process
         // optionally (TRT_TUNE_SMALL_PRE) the first passes, while there are thousands of clusters, run on the whole GPU (the neighbour
         // search of one pass over 2 035 clusters is 260 k box unions: 87 % of the single-CTA kernel's instructions); the tail of the loop,
         // the SAH report and the collapse run in one CTA.  Nothing comes back to the host in between: grids are sized for n, the count
