@@ -81,6 +81,18 @@ def test_c_host_program_renders_the_same_image(rt, tmp_path):
     img_sky, w, h = read_ppm(out)
     rt.scene_set(sky_sc)
     assert np.array_equal(img_sky, rt.render(S.params_for(sky_sc))["canva"]) and not np.array_equal(img_sky, img)
+    # the overrides of texture.h:71-87 as data: a scene file that drops them and sets one of its own == the same table through the Python mirror
+    cfg = tmp_path / "mini.cfg"
+    cfg.write_text(f"scene = sky\nobj = {os.path.join(MINI, 'mini.obj')}\nmtl = {os.path.join(MINI, 'mini.mtl')}\nwidth = 160\nspp = 16\nbounces = 6\n"
+                   "ao = 0\nvfov = 45\norigin = 2.2,1.6,3.0\ntarget = 0.0,0.5,0.0\nno-overrides\noverride = 3:alpha=0.3,index=1.4,reflection=0.5\n")
+    out = str(tmp_path / "mini_ov.ppm")
+    subprocess.check_call([exe, "--config", str(cfg), "--out", out], stdout=subprocess.DEVNULL)
+    img_ov, w, h = read_ppm(out)
+    ov_sc = mini_scene()
+    ov_sc.overrides = np.zeros(1, S.MAT_OVERRIDE)
+    ov_sc.overrides[0] = (3, S.OV_ALPHA | S.OV_MATERIAL_INDEX | S.OV_REFLECTION, S.BLACK, 0.0, 0.5, 0.3, 1.4)
+    rt.scene_set(ov_sc)
+    assert np.array_equal(img_ov, rt.render(S.params_for(ov_sc))["canva"]) and not np.array_equal(img_ov, img)
     # failure is reported, not a crash: missing texture
     bad = subprocess.run([exe, "--scene", "sky", "--obj", os.path.join(MINI, "mini.obj"), "--mtl", "/nonexistent.mtl"], capture_output=True, text=True)
     assert bad.returncode == 1 and "cannot open" in bad.stderr
