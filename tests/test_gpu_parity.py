@@ -318,6 +318,11 @@ def test_bit_identical_across_runs_and_sample_splits(rt):
     again = np.trunc(256.0 * np.clip(np.sqrt(hdr["radiance"].astype(np.float64)), 0.0, 0.999))
     assert np.abs(again - a["canva"]).max() <= 1 and (again != a["canva"]).mean() < 0.01
     assert np.abs(hdr["albedo"] - a["albedo"]).max() < 1e-6 and np.abs(hdr["normal"] - a["normal"]).max() < 1e-6
+    # the same float AOVs left on the DEVICE (trt_resolve_hdr_device: what a GPU denoiser consumes)
+    dev = torch.zeros(9 * n, dtype=torch.float32, device="cuda")
+    rt.resolve_hdr_device(S.params_for(sc, width=200, spp=40), total.data_ptr(), dev.data_ptr(), dev.data_ptr() + 12 * n, dev.data_ptr() + 24 * n)
+    got = dev.cpu().numpy().reshape(3, n, 3)
+    assert np.array_equal(got[0], hdr["radiance"]) and np.array_equal(got[1], hdr["albedo"]) and np.array_equal(got[2], hdr["normal"])
     # a different seed is a different image
     d = rt.render(S.params_for(sc, width=200, spp=40, seed=7))
     assert d["canva"].tobytes() != a["canva"].tobytes()
