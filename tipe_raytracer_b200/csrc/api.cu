@@ -44,6 +44,7 @@ struct DeviceCtx {
     // scene: grow-only device buffers, reused by every trt_scene_set (no cudaMalloc/cudaFree churn per frame)
     Buf sph_raw, tri_raw, quel_mat, sph, sph_mat, tri, tri_uv, tri_orig, nodes, texels, mats_raw, ov_raw, scratch, sky;
     Buf prehit;                                // engine 4: primary hits of the frame, 16 B per path
+    Buf nodes64;                               // experiment (TRT_TUNE_NODE64): 64-byte quantised nodes
     DevScene scene{};
     // work buffers
     unsigned long long* ctrs = nullptr;        // [0] item counter, [1..4] rays / box / tri / sphere tests
@@ -585,6 +586,7 @@ TRT_API void trt_destroy(trt_ctx* ctx)
         free_scene(d);
         d.sky.release();
         d.prehit.release();
+        d.nodes64.release();
         if (d.accum) cudaFree(d.accum);
         if (d.out) cudaFree(d.out);
         if (d.h_stage) cudaFreeHost(d.h_stage);
@@ -694,6 +696,11 @@ static int trt_scene_set_impl(trt_ctx* ctx,
     bo.sph = (float4*)d.sph.p; bo.sph_mat = (float4*)d.sph_mat.p; bo.tri = (float4*)d.tri.p; bo.tri_uv = (float4*)d.tri_uv.p;
     bo.tri_orig = (int*)d.tri_orig.p; bo.nodes = (float4*)d.nodes.p; bo.texels = (float4*)d.texels.p;
     CU(ctx, trt_build_scene(in, bo, d.stream));
+    const bool node64 = getenv("TRT_TUNE_NODE64") && atoi(getenv("TRT_TUNE_NODE64")) != 0 && bo.n_wide_nodes > 0;
+    if (node64) {
+        CU(ctx, d.nodes64.ensure((size_t)bo.n_wide_nodes * 64));
+        CU(ctx, trt_compress_nodes(bo.n_wide_nodes, bo.nodes, d.nodes64.p, d.stream));
+    }
     CU(ctx, cudaEventRecord(d.ev_c, d.stream));
     if (3 * bo.max_depth + 2 > TRT_STACK_DEPTH)
         return fail(ctx, TRT_ERR_INVALID, "BVH depth %d needs a traversal stack of %d entries (limit %d)", bo.max_depth, 3 * bo.max_depth + 2, TRT_STACK_DEPTH);
@@ -706,6 +713,7 @@ static int trt_scene_set_impl(trt_ctx* ctx,
         s.n_spheres = nbSpheres; s.sph = bo.sph; s.sph_mat = bo.sph_mat; s.sph64 = (const double*)d.sph_raw.p;
         s.n_tris = nbTriangles; s.tri = bo.tri; s.tri_uv = bo.tri_uv; s.tri_orig = bo.tri_orig; s.tri64 = (const double*)d.tri_raw.p;
         s.quel_mat = (const int*)d.quel_mat.p; s.nodes = bo.nodes; s.root = bo.root; s.n_nodes = bo.n_wide_nodes;
+        s.nodes64 = node64 ? (const float4*)d.nodes64.p : nullptr;
         s.texels = bo.texels; s.tex_w = tex_width; s.tex_h = tex_height; s.n_materials = nbMaterials;
         s.tri_tmin = bo.tri_tmin;
         s.root_lo = bo.root_lo; s.root_hi = bo.root_hi;
@@ -742,6 +750,7 @@ static int trt_scene_set_impl(trt_ctx* ctx,
         s.sph = (const float4*)q.sph.p; s.sph_mat = (const float4*)q.sph_mat.p; s.tri = (const float4*)q.tri.p; s.tri_uv = (const float4*)q.tri_uv.p;
         s.tri_orig = (const int*)q.tri_orig.p; s.nodes = (const float4*)q.nodes.p; s.texels = (const float4*)q.texels.p;
         s.sph64 = nullptr; s.tri64 = nullptr; s.quel_mat = nullptr;       // the FP64 primary pass (trt_primary) runs on the root only
+        s.nodes64 = nullptr;
     }
     for (auto& q : ctx->devs) { CU(ctx, cudaSetDevice(q.dev)); CU(ctx, cudaStreamSynchronize(q.stream)); }
     ctx->info.ms_build = now_ms() - t0;

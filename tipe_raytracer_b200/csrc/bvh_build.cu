@@ -593,11 +593,64 @@ build_small_kernel(int n, const int* __restrict__ ghead, const int* __restrict__
     }
 }
 
+// ---- 64-byte nodes (experiment, TRT_TUNE_NODE64): the four child boxes quantised to 8 bits per plane relative to the node's own box
+//   word 0-3 : origin.xyz (float), exponent bytes ex | ey << 8 | ez << 16 (scale_a = 2^(e_a - 127))
+//   word 4-7 : bytes lo.x[4] | hi.x[4] | lo.y[4] | hi.y[4]        word 8-9 : lo.z[4] | hi.z[4]        word 12-15 : child references
+// Planes are rounded outward by one extra step (the traversal folds the byte -> float conversion into the slab FMA, which costs
+// up to half a step of accuracy), so the quantised box always contains the exact one: it can only add node visits, never lose a hit.
+__global__ void compress_nodes(int n_nodes, const float4* __restrict__ nodes128, uint4* __restrict__ nodes64)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const float4* in = nodes128 + 8 * (size_t)i;
+    const int rot = i & 3;
+    float lo[3][4], hi[3][4]; int ref[4];
+    for (int a = 0; a < 3; a++) {
+        const float4 l = in[2 * ((a + rot) & 3)], h = in[2 * ((a + rot) & 3) + 1];
+        lo[a][0] = l.x; lo[a][1] = l.y; lo[a][2] = l.z; lo[a][3] = l.w; hi[a][0] = h.x; hi[a][1] = h.y; hi[a][2] = h.z; hi[a][3] = h.w;
+    }
+    { const float4 r = in[2 * ((3 + rot) & 3)]; ref[0] = __float_as_int(r.x); ref[1] = __float_as_int(r.y); ref[2] = __float_as_int(r.z); ref[3] = __float_as_int(r.w); }
+    float org[3]; unsigned ex[3]; unsigned qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+    for (int a = 0; a < 3; a++) {
+        float mn = 3.0e38f, mx = -3.0e38f;
+        for (int j = 0; j < 4; j++) if (ref[j] != 0x7ffffffe) { mn = fminf(mn, lo[a][j]); mx = fmaxf(mx, hi[a][j]); }
+        org[a] = mn;
+        // smallest power of two with (mx - mn) / scale <= 253: steps 1..254 hold the exact range, 0 and 255 the outward step
+        const float need = fmaxf((mx - mn) * (1.0f / 253.0f), 1e-30f);
+        int e = ((__float_as_int(need) >> 23) & 0xff) + 1;                   // 2^(e-127) > need
+        if (e < 1) e = 1; if (e > 254) e = 254;
+        ex[a] = (unsigned)e;
+        const float inv = __int_as_float((254 - e) << 23);                  // 2^-(e-127)
+        for (int j = 0; j < 4; j++) {
+            int l = 255, h = 0;                                              // unused slot (never read: its reference is EMPTY)
+            if (ref[j] != 0x7ffffffe) {
+                l = (int)floorf((lo[a][j] - mn) * inv) + 1 - 1;              // exact range in steps [0, 253]
+                h = (int)ceilf((hi[a][j] - mn) * inv) + 1 + 1;               // shifted by one step (origin moved down below) and rounded outward by one more
+                l = max(l, 0); h = min(h, 255);
+            }
+            qlo[a] |= (unsigned)l << (8 * j); qhi[a] |= (unsigned)h << (8 * j);
+        }
+        org[a] = mn - __int_as_float(e << 23);                              // the origin sits one step below the smallest plane: step 0 = mn - scale
+    }
+    uint4* out = nodes64 + 4 * (size_t)i;
+    out[0] = make_uint4(__float_as_uint(org[0]), __float_as_uint(org[1]), __float_as_uint(org[2]), ex[0] | (ex[1] << 8) | (ex[2] << 16));
+    out[1] = make_uint4(qlo[0], qhi[0], qlo[1], qhi[1]);
+    out[2] = make_uint4(qlo[2], qhi[2], 0u, 0u);
+    out[3] = make_uint4((unsigned)ref[0], (unsigned)ref[1], (unsigned)ref[2], (unsigned)ref[3]);
+}
+
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
 
 #define BT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return e_; } while (0)
+
+cudaError_t trt_compress_nodes(int n_nodes, const float4* nodes128, void* nodes64, cudaStream_t stream)
+{
+    if (n_nodes <= 0) return cudaSuccess;
+    compress_nodes<<<(n_nodes + 255) / 256, 256, 0, stream>>>(n_nodes, nodes128, (uint4*)nodes64);
+    return cudaGetLastError();
+}
 
 size_t trt_build_scratch_bytes(int n_tris)
 {

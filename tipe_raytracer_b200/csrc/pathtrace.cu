@@ -32,7 +32,7 @@
 // then leaves the loop as soon as fewer than exit_num/32 of its live lanes are still inside the BVH,
 // so that the lanes that are done get shaded and re-armed instead of idling.
 
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER, bool TOP = false, bool PREHIT = false>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER, bool TOP = false, bool PREHIT = false, bool N64 = false>
 __global__ void __launch_bounds__(PT_THREADS, HAS_TRIS ? PT_MIN_BLOCKS_MESH : PT_MIN_BLOCKS)
 pathtrace_kernel(const __grid_constant__ RenderArgs A)
 {
@@ -242,7 +242,7 @@ pathtrace_kernel(const __grid_constant__ RenderArgs A)
                 }
                 // if-if: every trip, each lane does whatever it is at — a node visit or a leaf test (measured faster than
                 // deferring, voting on or pairing the two on B200, profiles/README.md)
-                if (DEFER) bvh_trip_deferred<COUNT, TOP>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, A.defer, tr, pend, stack, cnt, 0, s_top, A.top_nodes);
+                if (DEFER) bvh_trip_deferred<COUNT, TOP, N64>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, A.defer, tr, pend, stack, cnt, 0, s_top, A.top_nodes);
                 else if (inside) bvh_step_unified<COUNT>(sc, P.o, rd, idir, ood, src_leaf, twin_leaf, ao, tr, stack, cnt);
             }
         }
@@ -372,7 +372,7 @@ cudaError_t trt_launch_primary_fp32(const RenderArgs& A, int* id, float* t, cuda
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false, bool TOP = false, bool PREHIT = false>
+template <bool HAS_TRIS, bool BRUTE, bool COUNT, bool DEFER = false, bool TOP = false, bool PREHIT = false, bool N64 = false>
 static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cudaStream_t stream)
 {
     {
@@ -383,14 +383,14 @@ static cudaError_t launch_variant(const RenderArgs& A, int grid, size_t smem, cu
         const char* v = getenv("TRT_TUNE_CARVEOUT");
         if (v && *v) pct = atoi(v);
         if (pct > 100) pct = 100;
-        cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT, N64>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         // more than ~460 spheres: the sphere table + the per-lane sums pass the 48 KB a kernel gets without asking
         if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaError_t e = cudaFuncSetAttribute(pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT, N64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
         }
     }
-    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT><<<grid, PT_THREADS, smem, stream>>>(A);
+    pathtrace_kernel<HAS_TRIS, BRUTE, COUNT, DEFER, TOP, PREHIT, N64><<<grid, PT_THREADS, smem, stream>>>(A);
     return cudaGetLastError();
 }
 
@@ -404,6 +404,8 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
                                       : launch_variant<false, false, false>(A, grid, smem, stream);
     if (brute) return count_tests ? launch_variant<true, true, true>(A, grid, smem, stream)
                                   : launch_variant<true, true, false>(A, grid, smem, stream);
+    if (A.scene.nodes64 && A.defer > 0 && !top && !A.prehit) return count_tests ? launch_variant<true, false, true, true, false, false, true>(A, grid, smem, stream)
+                                                                             : launch_variant<true, false, false, true, false, false, true>(A, grid, smem, stream);
     if (top) return launch_variant<true, false, false, true, true>(A, grid, smem, stream);
     if (A.prehit && A.defer > 0) return count_tests ? launch_variant<true, false, true, true, false, true>(A, grid, smem, stream)
                                                      : launch_variant<true, false, false, true, false, true>(A, grid, smem, stream);

@@ -41,6 +41,7 @@ struct DevScene {
     // child reference: >= 0 wide node, < 0 leaf ~(leaf position), TRT_CHILD_EMPTY unused slot;
     // the four 32-byte fields {x, y, z, children} of node i sit at slot (field + i) & 3 (L1 bank spreading)
     const float4* nodes;
+    const float4* nodes64;      // the same tree as 64-byte nodes with 8-bit quantised child boxes (experiment; nullptr = not built)
     int root;                   // 0, or ~0 when there is a single triangle
     float3 root_lo, root_hi;    // bounds of all triangles (rays that miss them never enter the traversal loop)
     // textures: nbMaterials slabs of tex_h*tex_w texels, 3 float4 per texel, overrides baked in

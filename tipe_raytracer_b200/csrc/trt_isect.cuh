@@ -288,7 +288,9 @@ __device__ __forceinline__ void bvh_step_unified(const DevScene& sc, float3 o, f
 // the result is unchanged.  Must be called by all 32 lanes.
 // TOP: the first top_k wide nodes (the top levels of the tree: the collapse numbers nodes level by level) were staged into
 // shared memory at kernel start (TMA bulk copy, pathtrace.cu) and are read from there, same rotated layout.
-template <bool COUNT, bool TOP = false>
+// N64: 64-byte nodes with 8-bit quantised child boxes (bvh_build.cu, compress_nodes) instead of the 128-byte ones: two 256-bit
+// loads per visit instead of four, and a byte -> float conversion folded into each slab FMA (experiment, TRT_TUNE_NODE64).
+template <bool COUNT, bool TOP = false, bool N64 = false>
 __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, float3 d, float3 idir, float3 ood,
                                                   int src_leaf, int twin_leaf, bool any_hit, int share,
                                                   Trav& tr, int& pend, int* stack, TraceCounters& cnt, int exp_flags = 0,
@@ -297,6 +299,42 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
     if (tr.node >= 0 && tr.node != TRT_TRAV_DONE) {
         TRT_CHECK(tr.node < sc.n_nodes, 101);
         TRT_CHECK(tr.sp >= 1 && tr.sp + 3 <= TRT_STACK_DEPTH, 102);
+        const float INF = __int_as_float(0x7f800000);
+        float k0, k1, k2, k3;
+        int r0, r1, r2, r3;
+        if (N64) {
+            const float4* rec = sc.nodes64 + 4 * (size_t)tr.node;
+            float4 w0, w1, w2, w3;
+            ldg256(rec, w0, w1); ldg256(rec + 2, w2, w3);
+            const unsigned ex = __float_as_uint(w0.w);
+            // plane = origin + step * 2^(e-127); t = (plane - o) * idir = step * A + B.  float(step) is formed as the bits 0x4B0000ss = 2^23 + ss
+            // (one PRMT), and the 2^23 is taken out again in the constant term (the half step this can cost is in the boxes' outward rounding)
+            const float Ax = __uint_as_float((ex & 0xffu) << 23) * idir.x, Ay = __uint_as_float(((ex >> 8) & 0xffu) << 23) * idir.y,
+                        Az = __uint_as_float(((ex >> 16) & 0xffu) << 23) * idir.z;
+            const float Bx = fmaf(-8388608.0f, Ax, fmaf(w0.x, idir.x, -ood.x)), By = fmaf(-8388608.0f, Ay, fmaf(w0.y, idir.y, -ood.y)),
+                        Bz = fmaf(-8388608.0f, Az, fmaf(w0.z, idir.z, -ood.z));
+            const unsigned lx = __float_as_uint(w1.x), hx = __float_as_uint(w1.y), ly = __float_as_uint(w1.z), hy = __float_as_uint(w1.w),
+                           lz = __float_as_uint(w2.x), hz = __float_as_uint(w2.y);
+            r0 = __float_as_int(w3.x); r1 = __float_as_int(w3.y); r2 = __float_as_int(w3.z); r3 = __float_as_int(w3.w);
+#define TRT_Q(WORD, SEL) __uint_as_float(__byte_perm(WORD, 0x4B000000u, SEL))
+#define TRT_SLAB64(SEL, REF, KEY)                                                                                  \
+    {                                                                                                              \
+        const float ax = fmaf(TRT_Q(lx, SEL), Ax, Bx), bx = fmaf(TRT_Q(hx, SEL), Ax, Bx);                          \
+        const float ay = fmaf(TRT_Q(ly, SEL), Ay, By), by = fmaf(TRT_Q(hy, SEL), Ay, By);                          \
+        const float az = fmaf(TRT_Q(lz, SEL), Az, Bz), bz = fmaf(TRT_Q(hz, SEL), Az, Bz);                          \
+        const float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), sc.box_tmin));            \
+        const float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tr.t));                   \
+        KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                                     \
+        if (COUNT && REF != TRT_CHILD_EMPTY) cnt.box_tests++;                                                      \
+    }
+            // __byte_perm selector: result bytes (b3 b2 b1 b0) = (magic.3, magic.2, magic.1, word.k) -> 0x7 6 5 k with the magic as the second operand
+            TRT_SLAB64(0x7650, r0, k0)
+            TRT_SLAB64(0x7651, r1, k1)
+            TRT_SLAB64(0x7652, r2, k2)
+            TRT_SLAB64(0x7653, r3, k3)
+#undef TRT_SLAB64
+#undef TRT_Q
+        } else {
         const int rot = tr.node & 3;
         float4 f0a, f0b, f1a, f1b, f2a, f2b, f3a, f3b;
         if (TOP && tr.node < top_k) {
@@ -308,7 +346,6 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
             ldg256(rec + 2 * ((0 + rot) & 3), f0a, f0b); ldg256(rec + 2 * ((1 + rot) & 3), f1a, f1b);
             ldg256(rec + 2 * ((2 + rot) & 3), f2a, f2b); ldg256(rec + 2 * ((3 + rot) & 3), f3a, f3b);
         }
-        const float INF = __int_as_float(0x7f800000);
 #define TRT_SLAB(LX, HX, LY, HY, LZ, HZ, REF, KEY)                                                        \
     {                                                                                                      \
         const float ax = fmaf(LX, idir.x, -ood.x), bx = fmaf(HX, idir.x, -ood.x);                          \
@@ -319,13 +356,13 @@ __device__ __forceinline__ void bvh_trip_deferred(const DevScene& sc, float3 o, 
         KEY = (tf >= tn && REF != TRT_CHILD_EMPTY) ? tn : INF;                                             \
         if (COUNT && REF != TRT_CHILD_EMPTY) cnt.box_tests++;                                               \
     }
-        float k0, k1, k2, k3;
-        int r0 = __float_as_int(f3a.x), r1 = __float_as_int(f3a.y), r2 = __float_as_int(f3a.z), r3 = __float_as_int(f3a.w);
+        r0 = __float_as_int(f3a.x); r1 = __float_as_int(f3a.y); r2 = __float_as_int(f3a.z); r3 = __float_as_int(f3a.w);
         TRT_SLAB(f0a.x, f0b.x, f1a.x, f1b.x, f2a.x, f2b.x, r0, k0)
         TRT_SLAB(f0a.y, f0b.y, f1a.y, f1b.y, f2a.y, f2b.y, r1, k1)
         TRT_SLAB(f0a.z, f0b.z, f1a.z, f1b.z, f2a.z, f2b.z, r2, k2)
         TRT_SLAB(f0a.w, f0b.w, f1a.w, f1b.w, f2a.w, f2b.w, r3, k3)
 #undef TRT_SLAB
+        }
         order2(k0, r0, k1, r1); order2(k2, r2, k3, r3);
         order2(k0, r0, k2, r2); order2(k1, r1, k3, r3);
         order2(k1, r1, k2, r2);

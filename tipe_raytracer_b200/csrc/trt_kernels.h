@@ -103,6 +103,8 @@ struct BuildOutputs {            // device buffers allocated by the caller with 
 };
 cudaError_t trt_build_scene(const BuildInputs& in, BuildOutputs& out, cudaStream_t stream);
 size_t trt_build_scratch_bytes(int n_tris);
+// experiment: the built 128-byte nodes as 64-byte nodes with 8-bit quantised child boxes (n_nodes * 64 bytes at nodes64)
+cudaError_t trt_compress_nodes(int n_nodes, const float4* nodes128, void* nodes64, cudaStream_t stream);
 
 // Known-answer kernels (leaf functions of K2 run over arrays).
 cudaError_t trt_kat_launch_sphere(int n, const float4* cr, const float* ray, int* hit, float* dst, float* point, float* normal, cudaStream_t s);
