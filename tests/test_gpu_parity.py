@@ -151,6 +151,17 @@ def test_render_c2_mesh_same_stream(rt, oracle):
     assert rt.bvh_info()["n_twins"] > 1000          # double-faced mesh: twins found
 
 
+def test_render_c2b_water_mesh_same_stream(rt, oracle):
+    """The second textured mesh SURVEY §8d names (model3D/water): single-faced, so no twins, 17 materials with light / glass / water ordinals."""
+    sc = S.water_mesh()
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    prim_g, prim_o = rt.primary(S.params_for(sc, width=200, spp=1)), oracle.primary(sc, S.params_for(sc, width=200, spp=1))
+    assert np.array_equal(prim_g["id"], prim_o["id"]) and np.array_equal(prim_g["t"], prim_o["t"]) and (prim_g["id"] >= 1).mean() > 0.2
+    a = rt.render(S.params_for(sc, width=96, spp=4, flags=FLAG_BRUTE_FORCE))
+    b = rt.render(S.params_for(sc, width=96, spp=4))
+    assert np.array_equal(a["canva"], b["canva"]) and a["stats"]["rays"] == b["stats"]["rays"]
+
+
 def test_render_c4_tree_same_stream(rt, oracle):
     sc = S.tree_mesh()
     _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)

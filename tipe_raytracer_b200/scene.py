@@ -271,6 +271,17 @@ def nature_mesh(fixture: Optional[str] = None) -> Scene:
                  width=1000, spp=200, bounces=4, use_ao=False)
 
 
+def water_mesh(fixture: Optional[str] = None) -> Scene:
+    """C2b, the secondary substitute SURVEY §8d names for the absent books mesh: model3D/water/mineways_tri.obj (1 740 triangles,
+    17 16x16 textures; NOT double-faced: no twins, unlike the nature mesh) + emissive sky; C2's knobs (200 spp, 4 bounces, AO off).
+    The built-in overrides make ordinal 1 a light, 3 glass and 4 water here too."""
+    tris, mats, tw, th, nb, quel = mesh_from_fixture(fixture or os.path.join(GOLDEN_DIR, "scene_water.npz"))
+    return Scene(name="water_mesh", spheres=spheres([sky_sphere()]), triangles=tris, mat_list=mats,
+                 tex_w=tw, tex_h=th, nb_materials=nb, quel_mat_pour_tri=quel,
+                 cam_origin=(2.8, 2.3, 3.6), cam_target=(0.0, 0.6, 0.0), vfov=40.0, ratio=4.0 / 3.0,
+                 width=1000, spp=200, bounces=4, use_ao=False)
+
+
 def tree_mesh(fixture: Optional[str] = None, grid: int = 1) -> Scene:
     """C4: 1st_mc_world/tree/tree_tri.obj (1 792 triangles, one 1024^2 RGBA texture) + emissive sky;
     1920x1080, 500 spp, 6 bounces.  grid > 1 instances the tree on a grid x grid lattice by
@@ -341,6 +352,7 @@ CONFIGS = {
     "C4": tree_mesh,
     "C5": readme_benchmark,
     "C3b": pyramide_eau,
+    "C2b": water_mesh,
     "C4sky": tree_mesh_sky,
     # BASELINE.md §4 "large triangle mesh": the tree instanced 24 x 24 times = 1 032 192 triangles (SYNTHETIC; the shipped
     # 1st_mc_world holds one 1 792-triangle tree), C4's resolution / bounces, camera pulled back to see the whole forest
