@@ -17,6 +17,7 @@
  *             [--config FILE]       a scene file: one `option = value` per line with the option names above (no dashes), `#` comments;
  *                                   the constants of main.c:293-347 become data.  Later command-line options win.
  *             [--dry-run]           print the resolved configuration and exit before touching the GPU
+ *             [--pageable-output]   canva / albedo_tab / normal_tab from calloc like main.c:385-400 (default: page-locked, trt_host_alloc)
  *             [--nranks N --rank R --id-file PATH [--device D]]   ONE PROCESS PER GPU: start N copies of this program with ranks
  *                                   0..N-1 and the same options; rank 0 writes the NCCL id to PATH, the others read it; every rank traces
  *                                   its share of the samples on GPU D (default R), the sums meet on rank 0 with ncclReduce, rank 0 writes the image
@@ -53,6 +54,7 @@ typedef struct config {
     const char *obj_file, *mtl_file, *out_file, *sky_file;
     unsigned long long seed; int n_gpus, truncate_like_main_c, tile_split, dry_run;
     int n_ranks, rank, device; const char* id_file;
+    int pageable_output;
     trt_sphere spheres[MAX_SPHERES]; int nbSpheres;
     trt_mat_override overrides[MAX_OVERRIDES]; int n_overrides;      /* starts as texture.h:71-87 */
 } config;
@@ -134,6 +136,7 @@ static int config_set(config* c, const char* name, const char* v, int depth)
     if (IS("tile-split")) { c->tile_split = 1; return 0; }
     if (IS("no-overrides")) { c->n_overrides = 0; return 0; }
     if (IS("dry-run")) { c->dry_run = 1; return 0; }
+    if (IS("pageable-output")) { c->pageable_output = 1; return 0; }
     if (!v) return -1;
     if (IS("scene")) {
         if (strcmp(v, "readme") == 0) { memcpy(c->spheres, README_SPHERES, sizeof README_SPHERES); c->nbSpheres = 10; }
@@ -172,7 +175,7 @@ static int config_set(config* c, const char* name, const char* v, int depth)
 
 static int is_flag(const char* name)
 {
-    return strcmp(name, "no-main-c-truncation") == 0 || strcmp(name, "tile-split") == 0 || strcmp(name, "no-overrides") == 0 || strcmp(name, "dry-run") == 0;
+    return strcmp(name, "no-main-c-truncation") == 0 || strcmp(name, "tile-split") == 0 || strcmp(name, "no-overrides") == 0 || strcmp(name, "dry-run") == 0 || strcmp(name, "pageable-output") == 0;
 }
 
 static int config_load_file(config* c, const char* path, int depth)
@@ -258,9 +261,19 @@ int main(int argc, char** argv)
 
     trt_camera cam = trt_init_camera(origin, target, up, vfov, ratio);
     size_t npix = (size_t)largeur_image * hauteur_image;
-    trt_vec3* canva = (trt_vec3*)calloc(npix, sizeof(trt_vec3));
-    trt_vec3* albedo_tab = (trt_vec3*)calloc(npix, sizeof(trt_vec3));
-    trt_vec3* normal_tab = (trt_vec3*)calloc(npix, sizeof(trt_vec3));
+    /* main.c:385-400 mallocs these three; page-locked memory from the library instead lets the GPUs write them directly over PCIe
+       (with N GPUs N bands at once).  --pageable-output keeps main.c's plain allocation: same image, staged copies. */
+    trt_vec3 *canva = NULL, *albedo_tab = NULL, *normal_tab = NULL;
+    int pinned_out = !cfg.pageable_output && trt_host_alloc(npix * sizeof(trt_vec3), (void**)&canva) == TRT_OK &&
+                     trt_host_alloc(npix * sizeof(trt_vec3), (void**)&albedo_tab) == TRT_OK && trt_host_alloc(npix * sizeof(trt_vec3), (void**)&normal_tab) == TRT_OK;
+    if (!pinned_out) {
+        trt_host_free(canva); trt_host_free(albedo_tab); trt_host_free(normal_tab);
+        canva = (trt_vec3*)calloc(npix, sizeof(trt_vec3));
+        albedo_tab = (trt_vec3*)calloc(npix, sizeof(trt_vec3));
+        normal_tab = (trt_vec3*)calloc(npix, sizeof(trt_vec3));
+    } else {
+        memset(canva, 0, npix * sizeof(trt_vec3)); memset(albedo_tab, 0, npix * sizeof(trt_vec3)); memset(normal_tab, 0, npix * sizeof(trt_vec3));
+    }
 
     /* ---- the replacement for main.c:402-453 -------------------------------------------------------------- */
     trt_ctx* ctx = NULL;
@@ -334,7 +347,9 @@ int main(int argc, char** argv)
 
     if (comm) trt_nccl_comm_destroy(comm);
     trt_destroy(ctx);
-    free(canva); free(albedo_tab); free(normal_tab); free(mat_list); free(sky_mat_list);
+    if (pinned_out) { trt_host_free(canva); trt_host_free(albedo_tab); trt_host_free(normal_tab); }
+    else { free(canva); free(albedo_tab); free(normal_tab); }
+    free(mat_list); free(sky_mat_list);
     trt_free_mesh(&mesh);
     return 0;
 }

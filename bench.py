@@ -365,6 +365,17 @@ def main():
         te_ms, e_rays = float(a[0]), float(b[1])
     e2e_value = e_rays / (te_ms * 1e-3) / 1e6
     e2e_hash = sha(host) if rank == 0 else None
+    # the same call with the three output arrays in page-locked memory (trt_host_alloc instead of main.c's malloc): the GPU
+    # writes them directly, no staging and no host copy threads.  Reported beside e2e, which keeps main.c's plain (pageable) arrays.
+    e2e_pinned = None
+    if world == 1 and not args.no_extras:
+        pinned = trt.host_arrays(npix, r.lib)
+        host_keep, host = host, pinned
+        step_e2e()
+        tp_ms, pst = timed(step_e2e, e2e_steps)
+        e2e_pinned = {"value": float(sum(s["rays"] for s in pst)) / (tp_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": tp_ms / e2e_steps, "steps": e2e_steps,
+                      "same_image": bool(sha(pinned) == e2e_hash), "what": "as e2e, output arrays from trt_host_alloc (page-locked)"}
+        host = host_keep
 
     # ---- extras (outside the timed regions above) -------------------------------------------------------
     extras = {}
@@ -479,6 +490,8 @@ def main():
             "roofline": roofline, "bvh": r.bvh_info(),
         }
         line.update(extras)
+        if e2e_pinned:
+            line["e2e_page_locked_outputs"] = e2e_pinned
         if cpu:
             line["cpu_baseline"] = cpu
         json_out.write(json.dumps(line) + "\n")

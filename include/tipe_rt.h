@@ -219,6 +219,12 @@ TRT_API int trt_reduce_nccl(trt_ctx* ctx, void* comm, int64_t* d_accum, size_t c
  * NULL there).  The image is bit-identical to trt_render on one GPU.  stats describe this rank's share. */
 TRT_API int trt_render_distributed(trt_ctx* ctx, const trt_params* params, void* nccl_comm, int rank, int n_ranks,
                                    trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, trt_stats* stats);
+/* Optional: page-locked host memory for canva / albedo_tab / normal_tab (instead of the three malloc()s of main.c:385-400).  When all
+ * three arrays of a render / resolve call are page-locked (these, or cudaHostAlloc / cudaHostRegister of the caller's own), the GPUs
+ * write them directly over PCIe - with N devices N bands at once - instead of going through the library's staging buffer and
+ * host copy threads.  Ordinary malloc()ed arrays keep working as before. */
+TRT_API int  trt_host_alloc(size_t bytes, void** out);
+TRT_API void trt_host_free(void* p);
 /* CUDA ordinal of the ctx's k-th device (-1 if out of range) */
 TRT_API int trt_device_of(const trt_ctx* ctx, int k);
 

@@ -242,3 +242,17 @@ def test_c_host_program_one_process_per_gpu(rt, tmp_path):
                                   stdout=subprocess.DEVNULL) for r in (1, 0)]
         assert [p.wait(timeout=120) for p in procs] == [0, 0]
         assert open(out).read() == open(one).read()
+
+
+def test_page_locked_output_arrays_are_written_directly(rt):
+    """trt_host_alloc'ed canva / albedo_tab / normal_tab: the GPU writes them over PCIe without the staging buffer; same values as into
+    ordinary numpy arrays, on a frame large enough for the staged path (>= 8 MB) and on a small one."""
+    sc = S.cornell_spheres()
+    rt.scene_set(sc)
+    for width, spp in ((640, 4), (64, 6)):
+        rp = S.params_for(sc, width=width, spp=spp)
+        a = rt.render(rp)
+        pinned = trt.host_arrays(rp.width * rp.height, rt.lib)
+        b = rt.render(rp, out=pinned)
+        for k in ("canva", "albedo", "normal"):
+            assert b[k] is pinned[k] and a[k].tobytes() == b[k].tobytes()

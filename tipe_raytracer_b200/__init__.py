@@ -29,7 +29,7 @@ ACCUM_CHANNELS, ACCUM_FRAC_BITS = 9, 28
 ABI_SYMBOLS = [
     "trt_default_overrides", "trt_init", "trt_destroy", "trt_last_error", "trt_version",
     "trt_scene_set", "trt_sky_set", "trt_render", "trt_primary", "trt_primary_fp32", "trt_accumulate", "trt_resolve", "trt_resolve_device", "trt_resolve_hdr", "trt_resolve_hdr_device",
-    "trt_nccl_version", "trt_nccl_unique_id", "trt_nccl_comm_init", "trt_nccl_comm_destroy", "trt_reduce_nccl", "trt_device_of", "trt_render_distributed",
+    "trt_nccl_version", "trt_nccl_unique_id", "trt_nccl_comm_init", "trt_nccl_comm_destroy", "trt_reduce_nccl", "trt_device_of", "trt_render_distributed", "trt_host_alloc", "trt_host_free",
     "trt_stream", "trt_synchronize", "trt_bvh_info_get", "trt_debug_schedule",
     "trt_kat_hit_sphere", "trt_kat_hit_triangle", "trt_kat_refract", "trt_kat_philox", "trt_kat_tonemap",
 ]
@@ -107,6 +107,20 @@ def load_library() -> C.CDLL:
     for name in ABI_SYMBOLS:
         getattr(lib, name)
     return lib
+
+
+def host_arrays(n_pixels: int, lib: Optional[C.CDLL] = None) -> dict:
+    """canva / albedo / normal [n_pixels, 3] float64 in PAGE-LOCKED host memory (trt_host_alloc): the GPUs write them directly."""
+    lib = lib or load_library()
+    out = {}
+    for k in ("canva", "albedo", "normal"):
+        p = C.c_void_p()
+        rc = lib.trt_host_alloc(C.c_size_t(n_pixels * 24), C.byref(p))
+        if rc != 0:
+            raise TrtError(f"trt_host_alloc failed ({rc})")
+        buf = (C.c_double * (3 * n_pixels)).from_address(p.value)
+        out[k] = np.frombuffer(buf, dtype=np.float64).reshape(n_pixels, 3)
+    return out          # (kept for the life of the process; trt_host_free(ptr) releases one)
 
 
 def _ptr(a):

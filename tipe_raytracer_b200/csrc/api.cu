@@ -132,12 +132,13 @@ void ensure_stage(DeviceCtx& d, size_t bytes)
 {
     const char* v = getenv("TRT_TUNE_STAGED");
     if (v && *v && atoi(v) == 0) return;
+    if (bytes < COPY_CHUNK) return;                 // small frames: plain copies
     if (d.stage_bytes >= bytes) return;
     if (d.h_stage) cudaFreeHost(d.h_stage);
     d.h_stage = nullptr; d.stage_bytes = 0;
     if (cudaHostAlloc((void**)&d.h_stage, bytes, cudaHostAllocDefault) == cudaSuccess) d.stage_bytes = bytes;
     else { d.h_stage = nullptr; cudaGetLastError(); }
-    const size_t n_chunks = (bytes + COPY_CHUNK - 1) / COPY_CHUNK;
+    const size_t n_chunks = (bytes + COPY_CHUNK - 1) / COPY_CHUNK + 1;      // + the chunk of canva bytes
     while (d.chunk_ev.size() < n_chunks) {
         cudaEvent_t e = nullptr;
         if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); break; }
@@ -150,69 +151,109 @@ void ensure_stage(DeviceCtx& d, size_t bytes)
 size_t canva8_bytes(size_t npix) { return (3 * npix + 255) & ~(size_t)255; }
 
 // d.out -> the caller's three arrays (canva widened to doubles on the way), then waits for the stream.
-int copy_out(trt_ctx* ctx, DeviceCtx& d, size_t npix, trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab)
+// Two halves, so that several devices can have their copies in flight before the host starts draining the first one:
+// copy_out_issue enqueues the device -> pinned-staging copies (one event per chunk) and returns whether the staged path is used;
+// copy_out_drain moves what arrives into the caller's arrays (canva widened to doubles) and waits for the stream.
+bool copy_out_issue(trt_ctx* ctx, DeviceCtx& d, size_t npix, int* rc_out)
 {
+    *rc_out = TRT_OK;
     const size_t c8 = canva8_bytes(npix), part = sizeof(double) * 3 * npix, total = c8 + 2 * part;
     const size_t n_chunks = 1 + (2 * part + COPY_CHUNK - 1) / COPY_CHUNK;
-    const bool staged = d.h_stage && d.stage_bytes >= total && d.chunk_ev.size() >= n_chunks && total >= 4 * COPY_CHUNK;
+    const bool staged = d.h_stage && d.stage_bytes >= total && d.chunk_ev.size() >= n_chunks && total >= COPY_CHUNK;
+    if (!staged) return false;
     const char* src = (const char*)d.out;
-    auto widen = [](double* dst, const unsigned char* s8, size_t count) { for (size_t k = 0; k < count; k++) dst[k] = (double)s8[k]; };
-    if (!staged) {
-        std::vector<unsigned char> tmp(canva ? 3 * npix : 0);
-        if (canva) CU(ctx, cudaMemcpyAsync(tmp.data(), src, 3 * npix, cudaMemcpyDeviceToHost, d.stream));
-        if (albedo_tab) CU(ctx, cudaMemcpyAsync(albedo_tab, src + c8, part, cudaMemcpyDeviceToHost, d.stream));
-        if (normal_tab) CU(ctx, cudaMemcpyAsync(normal_tab, src + c8 + part, part, cudaMemcpyDeviceToHost, d.stream));
-        CU(ctx, cudaStreamSynchronize(d.stream));
-        if (canva) widen((double*)canva, tmp.data(), 3 * npix);
-        return TRT_OK;
-    }
+    auto step = [&](cudaError_t e) { if (e != cudaSuccess && *rc_out == TRT_OK) *rc_out = fail(ctx, TRT_ERR_CUDA, "device -> host copy failed: %s", cudaGetErrorString(e)); };
     // chunk 0 = the canva bytes (they arrive first and every thread widens a slice of them), chunks 1.. = 2 MB pieces of the two AOV tables
     const size_t n_aov = (2 * part + COPY_CHUNK - 1) / COPY_CHUNK;
-    CU(ctx, cudaMemcpyAsync(d.h_stage, src, c8, cudaMemcpyDeviceToHost, d.stream));
-    CU(ctx, cudaEventRecord(d.chunk_ev[0], d.stream));
+    step(cudaMemcpyAsync(d.h_stage, src, c8, cudaMemcpyDeviceToHost, d.stream));
+    step(cudaEventRecord(d.chunk_ev[0], d.stream));
     for (size_t c = 0; c < n_aov; c++) {
         const size_t off = c8 + c * COPY_CHUNK, len = (c + 1) * COPY_CHUNK <= 2 * part ? COPY_CHUNK : 2 * part - c * COPY_CHUNK;
-        CU(ctx, cudaMemcpyAsync(d.h_stage + off, src + off, len, cudaMemcpyDeviceToHost, d.stream));
-        CU(ctx, cudaEventRecord(d.chunk_ev[1 + c], d.stream));
+        step(cudaMemcpyAsync(d.h_stage + off, src + off, len, cudaMemcpyDeviceToHost, d.stream));
+        step(cudaEventRecord(d.chunk_ev[1 + c], d.stream));
     }
-    // the host side (bytes -> doubles, staging -> the caller's pageable arrays) is the slow half, not PCIe; measured on the B200 box's
-    // 16-core host for C2's 750 000 pixels: 1 thread 5.6 ms, 2: 3.0, 4: 2.0, 8: 1.3, 16: 1.15
-    int n_threads = 16;
-    { const unsigned hc = std::thread::hardware_concurrency(); if (hc > 0 && (int)hc < n_threads) n_threads = (int)hc; }
-    { const char* v = getenv("TRT_TUNE_COPY_THREADS"); if (v && *v) n_threads = atoi(v); }
-    if (n_threads < 1) n_threads = 1;
-    if (n_threads > 16) n_threads = 16;
-    cudaError_t errs[16];
-    char* aov_dst[2] = {(char*)albedo_tab, (char*)normal_tab};
-    auto worker = [&](int t) {
-        errs[t] = cudaSetDevice(d.dev);
-        if (errs[t] == cudaSuccess) errs[t] = cudaEventSynchronize(d.chunk_ev[0]);
-        if (errs[t] == cudaSuccess && canva) {
-            const size_t n8 = 3 * npix, lo = n8 * (size_t)t / (size_t)n_threads, hi = n8 * (size_t)(t + 1) / (size_t)n_threads;
-            widen((double*)canva + lo, (const unsigned char*)d.h_stage + lo, hi - lo);
+    return true;
+}
+
+// One band of the image on one device, on its way to the caller's arrays (pointers already offset to the band).
+struct OutJob {
+    DeviceCtx* d; size_t nb; int mode;                     // mode: 0 plain copies, 1 staged (copy_out_issue), 2 direct into page-locked arrays
+    trt_vec3 *canva, *albedo_tab, *normal_tab;
+};
+
+// Finishes all jobs: ONE team of host threads drains the staged bands of all devices (a thread per band and device would spend
+// more time being created than copying), then every stream is waited for.
+int drain_jobs(trt_ctx* ctx, const OutJob* jobs, int n_jobs)
+{
+    auto widen = [](double* dst, const unsigned char* s8, size_t count) { for (size_t k = 0; k < count; k++) dst[k] = (double)s8[k]; };
+    bool any_staged = false;
+    for (int j = 0; j < n_jobs; j++) {
+        const OutJob& J = jobs[j];
+        if (J.nb == 0) continue;
+        if (J.mode == 1) { any_staged = true; continue; }
+        CU(ctx, cudaSetDevice(J.d->dev));
+        if (J.mode == 0) {
+            const size_t c8 = canva8_bytes(J.nb), part = sizeof(double) * 3 * J.nb;
+            const char* src = (const char*)J.d->out;
+            std::vector<unsigned char> tmp(J.canva ? 3 * J.nb : 0);
+            if (J.canva) CU(ctx, cudaMemcpyAsync(tmp.data(), src, 3 * J.nb, cudaMemcpyDeviceToHost, J.d->stream));
+            if (J.albedo_tab) CU(ctx, cudaMemcpyAsync(J.albedo_tab, src + c8, part, cudaMemcpyDeviceToHost, J.d->stream));
+            if (J.normal_tab) CU(ctx, cudaMemcpyAsync(J.normal_tab, src + c8 + part, part, cudaMemcpyDeviceToHost, J.d->stream));
+            CU(ctx, cudaStreamSynchronize(J.d->stream));
+            if (J.canva) widen((double*)J.canva, tmp.data(), 3 * J.nb);
         }
-        for (size_t c = (size_t)t; c < n_aov && errs[t] == cudaSuccess; c += (size_t)n_threads) {
-            errs[t] = cudaEventSynchronize(d.chunk_ev[1 + c]);
-            size_t off = c * COPY_CHUNK;
-            const size_t end = (c + 1) * COPY_CHUNK <= 2 * part ? (c + 1) * COPY_CHUNK : 2 * part;
-            while (off < end && errs[t] == cudaSuccess) {          // a chunk may straddle the two tables
-                const size_t a = off / part, in = off - a * part, len = (end - off < part - in) ? end - off : part - in;
-                if (aov_dst[a]) memcpy(aov_dst[a] + in, d.h_stage + c8 + off, len);
-                off += len;
+    }
+    if (any_staged) {
+        // the host side (bytes -> doubles, staging -> the caller's pageable arrays) is the slow half, not PCIe; measured on the B200 box's
+        // 16-core host for C2's 750 000 pixels: 1 thread 5.6 ms, 2: 3.0, 4: 2.0, 8: 1.3, 16: 1.15
+        int n_threads = 16;
+        { const unsigned hc = std::thread::hardware_concurrency(); if (hc > 0 && (int)hc < n_threads) n_threads = (int)hc; }
+        { const char* v = getenv("TRT_TUNE_COPY_THREADS"); if (v && *v) n_threads = atoi(v); }
+        if (n_threads < 1) n_threads = 1;
+        if (n_threads > 16) n_threads = 16;
+        cudaError_t errs[16];
+        auto worker = [&](int t) {
+            errs[t] = cudaSuccess;
+            for (int j = 0; j < n_jobs && errs[t] == cudaSuccess; j++) {
+                const OutJob& J = jobs[j];
+                if (J.nb == 0 || J.mode != 1) continue;
+                DeviceCtx& d = *J.d;
+                const size_t c8 = canva8_bytes(J.nb), part = sizeof(double) * 3 * J.nb, n_aov = (2 * part + COPY_CHUNK - 1) / COPY_CHUNK;
+                char* aov_dst[2] = {(char*)J.albedo_tab, (char*)J.normal_tab};
+                errs[t] = cudaSetDevice(d.dev);
+                if (errs[t] == cudaSuccess) errs[t] = cudaEventSynchronize(d.chunk_ev[0]);
+                if (errs[t] == cudaSuccess && J.canva) {
+                    const size_t n8 = 3 * J.nb, lo = n8 * (size_t)t / (size_t)n_threads, hi = n8 * (size_t)(t + 1) / (size_t)n_threads;
+                    widen((double*)J.canva + lo, (const unsigned char*)d.h_stage + lo, hi - lo);
+                }
+                for (size_t c = (size_t)t; c < n_aov && errs[t] == cudaSuccess; c += (size_t)n_threads) {
+                    errs[t] = cudaEventSynchronize(d.chunk_ev[1 + c]);
+                    size_t off = c * COPY_CHUNK;
+                    const size_t end = (c + 1) * COPY_CHUNK <= 2 * part ? (c + 1) * COPY_CHUNK : 2 * part;
+                    while (off < end && errs[t] == cudaSuccess) {          // a chunk may straddle the two tables
+                        const size_t a = off / part, in = off - a * part, len = (end - off < part - in) ? end - off : part - in;
+                        if (aov_dst[a]) memcpy(aov_dst[a] + in, d.h_stage + c8 + off, len);
+                        off += len;
+                    }
+                }
             }
+        };
+        std::thread th[15];
+        int started = 1;
+        try {
+            for (int t = 1; t < n_threads; t++) { th[t - 1] = std::thread(worker, t); started = t + 1; }
+        } catch (...) {                                     // thread creation failed: never let an exception cross the C ABI; the missing shares are done here
         }
-    };
-    std::thread th[15];
-    int started = 1;
-    try {
-        for (int t = 1; t < n_threads; t++) { th[t - 1] = std::thread(worker, t); started = t + 1; }
-    } catch (...) {                                     // thread creation failed: never let an exception cross the C ABI; the missing shares are done here
+        worker(0);
+        for (int t = 1; t < started; t++) th[t - 1].join();
+        for (int t = started; t < n_threads; t++) worker(t);
+        for (int t = 0; t < n_threads; t++) CU(ctx, errs[t]);
     }
-    worker(0);
-    for (int t = 1; t < started; t++) th[t - 1].join();
-    for (int t = started; t < n_threads; t++) worker(t);
-    for (int t = 0; t < n_threads; t++) CU(ctx, errs[t]);
-    CU(ctx, cudaStreamSynchronize(d.stream));
+    for (int j = 0; j < n_jobs; j++) {
+        if (jobs[j].nb == 0) continue;
+        CU(ctx, cudaSetDevice(jobs[j].d->dev));
+        CU(ctx, cudaStreamSynchronize(jobs[j].d->stream));
+    }
     return TRT_OK;
 }
 
@@ -493,6 +534,17 @@ int trt_set_error(trt_ctx* ctx, int code, const char* text) { return fail(ctx, c
 // ================================================================================================
 extern "C" {
 
+TRT_API int trt_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return TRT_ERR_INVALID;
+    *out = nullptr;
+    const cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; return fail(nullptr, e == cudaErrorMemoryAllocation ? TRT_ERR_OOM : TRT_ERR_CUDA, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e)); }
+    return TRT_OK;
+}
+
+TRT_API void trt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 TRT_API int trt_device_of(const trt_ctx* ctx, int k) { return (ctx && k >= 0 && k < (int)ctx->devs.size()) ? ctx->devs[k].dev : -1; }
 
 TRT_API int trt_version(void) { return 100; }
@@ -551,20 +603,19 @@ TRT_API int trt_init(const int* device_ids, int n_devices, trt_ctx** out)
         d.n_sms = prop.multiProcessorCount;
         memset(d.h_ctrs, 0, sizeof(unsigned long long) * 16);
     }
-    // peer access root <- others, for the fused reduce+resolve
-    for (size_t k = 1; k < ctx->devs.size(); k++) {
-        int can = 0;
-        cudaDeviceCanAccessPeer(&can, ctx->devs[0].dev, ctx->devs[k].dev);
-        if (!can) { fail(nullptr, TRT_ERR_CUDA, "device %d cannot map device %d's memory (no NVLink/P2P)", ctx->devs[0].dev, ctx->devs[k].dev); trt_destroy(ctx); return TRT_ERR_CUDA; }
-        cudaSetDevice(ctx->devs[0].dev);
-        e = cudaDeviceEnablePeerAccess(ctx->devs[k].dev, 0);
-        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { fail(nullptr, TRT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); trt_destroy(ctx); return TRT_ERR_CUDA; }
-        cudaGetLastError();
-        // and the other way, so that the scene built on the root goes to the peers over NVLink (cudaMemcpyPeerAsync, trt_scene_set)
-        cudaSetDevice(ctx->devs[k].dev);
-        cudaDeviceEnablePeerAccess(ctx->devs[0].dev, 0);
-        cudaGetLastError();
-    }
+    // peer access between every pair of the ctx's devices: every device resolves its own band of the image from the sums of all of
+    // them (trt_render), and the built scene goes from the first device to the others over NVLink (trt_scene_set)
+    for (size_t i = 0; i < ctx->devs.size(); i++)
+        for (size_t j = 0; j < ctx->devs.size(); j++) {
+            if (i == j) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, ctx->devs[i].dev, ctx->devs[j].dev);
+            if (!can) { fail(nullptr, TRT_ERR_CUDA, "device %d cannot map device %d's memory (no NVLink/P2P)", ctx->devs[i].dev, ctx->devs[j].dev); trt_destroy(ctx); return TRT_ERR_CUDA; }
+            cudaSetDevice(ctx->devs[i].dev);
+            e = cudaDeviceEnablePeerAccess(ctx->devs[j].dev, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { fail(nullptr, TRT_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); trt_destroy(ctx); return TRT_ERR_CUDA; }
+            cudaGetLastError();
+        }
     *out = ctx;
     return TRT_OK;
 }
@@ -822,17 +873,68 @@ TRT_API int trt_accumulate(trt_ctx* ctx, const trt_params* params, int64_t* d_ac
 }
 
 static int resolve_common(trt_ctx* ctx, const trt_params* p, const long long* const* srcs, int n_src,
-                          double* d_canva, double* d_albedo, double* d_normal, unsigned char* d_canva8 = nullptr)
+                          double* d_canva, double* d_albedo, double* d_normal, unsigned char* d_canva8 = nullptr,
+                          DeviceCtx* dev = nullptr, size_t p0 = 0, size_t p1 = 0)
 {
-    DeviceCtx& d = ctx->devs[0];
+    DeviceCtx& d = dev ? *dev : ctx->devs[0];
     ResolveArgs R{};
     R.W = p->largeur_image; R.H = p->hauteur_image;
     R.divisor = p->sample_total > 0 ? p->sample_total : p->nbRayonParPixel;
     R.n_src = n_src;
     for (int k = 0; k < n_src; k++) R.src[k] = srcs[k];
+    R.p0 = p0; R.p1 = p1 > p0 ? p1 : (size_t)R.W * (size_t)R.H;
     R.canva = d_canva; R.albedo = d_albedo; R.normal = d_normal; R.canva8 = d_canva8;
     CU(ctx, trt_launch_resolve(R, d.n_sms, d.stream));
     return TRT_OK;
+}
+
+// Is this host pointer page-locked (trt_host_alloc, cudaHostAlloc, cudaHostRegister)?  Then the DMA engine can write it directly.
+static bool host_is_pinned(const void* p)
+{
+    if (!p) return false;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// Tonemap pixels [p0, p1) on device d and start sending them to the caller's arrays (pointers already offset to p0).
+//   mode 2: all three arrays are page-locked: canva is written as doubles and the three bands are copied straight into the caller's
+//           memory by the DMA engine (no staging, no host threads: with N devices the N bands cross N PCIe links at once);
+//   mode 1: pageable arrays, large: canva as bytes + AOV tables through the pinned staging ring (copy_out_issue / copy_out_drain);
+//   mode 0: pageable arrays, small: plain copies in out_finish.
+static int resolve_and_send(trt_ctx* ctx, const trt_params* rp, const long long* const* srcs, int n_src, DeviceCtx& d, size_t p0, size_t p1,
+                            trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab, int* mode)
+{
+    const size_t nb = p1 - p0;
+    int rc;
+    *mode = 0;
+    if (nb == 0) return TRT_OK;
+    const char* v = getenv("TRT_TUNE_DIRECT_D2H");
+    const bool direct = !(v && *v && atoi(v) == 0) && host_is_pinned(canva) && host_is_pinned(albedo_tab) && host_is_pinned(normal_tab);
+    if (direct) {
+        double* ob = d.out;
+        if ((rc = resolve_common(ctx, rp, srcs, n_src, ob, ob + 3 * nb, ob + 6 * nb, nullptr, &d, p0, p1)) != TRT_OK) return rc;
+        CU(ctx, cudaEventRecord(d.ev_d, d.stream));
+        const size_t part = sizeof(double) * 3 * nb;
+        CU(ctx, cudaMemcpyAsync(canva, ob, part, cudaMemcpyDeviceToHost, d.stream));
+        CU(ctx, cudaMemcpyAsync(albedo_tab, ob + 3 * nb, part, cudaMemcpyDeviceToHost, d.stream));
+        CU(ctx, cudaMemcpyAsync(normal_tab, ob + 6 * nb, part, cudaMemcpyDeviceToHost, d.stream));
+        *mode = 2;
+        return TRT_OK;
+    }
+    char* ob = (char*)d.out;
+    if ((rc = resolve_common(ctx, rp, srcs, n_src, nullptr, (double*)(ob + canva8_bytes(nb)), (double*)(ob + canva8_bytes(nb)) + 3 * nb,
+                             (unsigned char*)ob, &d, p0, p1)) != TRT_OK) return rc;
+    CU(ctx, cudaEventRecord(d.ev_d, d.stream));
+    rc = TRT_OK;
+    *mode = copy_out_issue(ctx, d, nb, &rc) ? 1 : 0;
+    return rc;
+}
+
+static int out_finish(trt_ctx* ctx, DeviceCtx& d, size_t nb, int mode, trt_vec3* canva, trt_vec3* albedo_tab, trt_vec3* normal_tab)
+{
+    const OutJob job = {&d, nb, mode, canva, albedo_tab, normal_tab};
+    return drain_jobs(ctx, &job, 1);
 }
 
 TRT_API int trt_resolve_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
@@ -860,11 +962,10 @@ static int trt_resolve_impl(trt_ctx* ctx, const trt_params* params, const int64_
     CU(ctx, cudaSetDevice(d.dev));
     if ((rc = ensure_out(ctx, d, npix)) != TRT_OK) return rc;
     const long long* src = (const long long*)d_accum;
-    char* ob = (char*)d.out;
-    rc = resolve_common(ctx, params, &src, 1, nullptr, (double*)(ob + canva8_bytes(npix)), (double*)(ob + canva8_bytes(npix)) + 3 * npix, (unsigned char*)ob);
-    if (rc != TRT_OK) return rc;
-    if (canva && albedo_tab && normal_tab) ensure_stage(d, sizeof(double) * 9 * npix);
-    return copy_out(ctx, d, npix, canva, albedo_tab, normal_tab);
+    if (!(host_is_pinned(canva) && host_is_pinned(albedo_tab) && host_is_pinned(normal_tab))) ensure_stage(d, sizeof(double) * 9 * npix);
+    int mode = 0;
+    if ((rc = resolve_and_send(ctx, params, &src, 1, d, 0, npix, canva, albedo_tab, normal_tab, &mode)) != TRT_OK) return rc;
+    return out_finish(ctx, d, npix, mode, canva, albedo_tab, normal_tab);
 }
 
 TRT_API int trt_resolve_hdr_device(trt_ctx* ctx, const trt_params* params, const int64_t* d_accum,
@@ -936,19 +1037,37 @@ static int trt_render_impl(trt_ctx* ctx, const trt_params* params,
         CU(ctx, cudaEventRecord(d.ev_c, d.stream));
         srcs.push_back(d.accum);
     }
-    if (canva && albedo_tab && normal_tab) { cudaSetDevice(ctx->devs[0].dev); ensure_stage(ctx->devs[0], sizeof(double) * 9 * npix); }   // while the GPUs trace
-    // root: wait for the peers, then reduce over NVLink peer mappings while tonemapping
+    // Every device resolves its own BAND of the image (pixels [npix*k/N, npix*(k+1)/N)): it reads that band of every device's int64
+    // sums over NVLink peer mappings while it tonemaps (the reduction is fused into the resolve and spread over all devices and
+    // all their NVLink ports), then sends its band to the host over its own PCIe link; the host drains the bands one after the other
+    // while the later ones are still arriving.
     DeviceCtx& root = ctx->devs[0];
-    CU(ctx, cudaSetDevice(root.dev));
-    if ((rc = ensure_out(ctx, root, npix)) != TRT_OK) return rc;
-    for (int k = 1; k < n_dev; k++) CU(ctx, cudaStreamWaitEvent(root.stream, ctx->devs[k].ev_c, 0));
     trt_params rp = *params;
     if (rp.sample_total <= 0) rp.sample_total = spp;
-    char* ob = (char*)root.out;
-    if ((rc = resolve_common(ctx, &rp, srcs.data(), n_dev, nullptr, (double*)(ob + canva8_bytes(npix)), (double*)(ob + canva8_bytes(npix)) + 3 * npix, (unsigned char*)ob)) != TRT_OK) return rc;
-    launches++;
-    CU(ctx, cudaEventRecord(root.ev_d, root.stream));
-    if ((rc = copy_out(ctx, root, npix, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;
+    const bool all_pinned = host_is_pinned(canva) && host_is_pinned(albedo_tab) && host_is_pinned(normal_tab);      // then no staging buffer is needed
+    std::vector<size_t> band(n_dev + 1);
+    for (int k = 0; k <= n_dev; k++) band[k] = npix * (size_t)k / (size_t)n_dev;
+    for (int k = 0; k < n_dev; k++) {                      // while the GPUs trace: output and staging buffers for the bands
+        DeviceCtx& d = ctx->devs[k];
+        const size_t nb = band[k + 1] - band[k];
+        CU(ctx, cudaSetDevice(d.dev));
+        if ((rc = ensure_out(ctx, d, nb)) != TRT_OK) return rc;
+        if (!all_pinned) ensure_stage(d, sizeof(double) * 9 * nb);
+    }
+    std::vector<int> mode(n_dev, 0);
+    for (int k = 0; k < n_dev; k++) {
+        DeviceCtx& d = ctx->devs[k];
+        CU(ctx, cudaSetDevice(d.dev));
+        for (int j = 0; j < n_dev; j++) if (j != k) CU(ctx, cudaStreamWaitEvent(d.stream, ctx->devs[j].ev_c, 0));
+        if ((rc = resolve_and_send(ctx, &rp, srcs.data(), n_dev, d, band[k], band[k + 1], canva ? canva + band[k] : nullptr,
+                                   albedo_tab ? albedo_tab + band[k] : nullptr, normal_tab ? normal_tab + band[k] : nullptr, &mode[k])) != TRT_OK) return rc;
+        launches++;
+    }
+    std::vector<OutJob> jobs(n_dev);
+    for (int k = 0; k < n_dev; k++)
+        jobs[k] = OutJob{&ctx->devs[k], band[k + 1] - band[k], mode[k], canva ? canva + band[k] : nullptr,
+                         albedo_tab ? albedo_tab + band[k] : nullptr, normal_tab ? normal_tab + band[k] : nullptr};
+    if ((rc = drain_jobs(ctx, jobs.data(), n_dev)) != TRT_OK) return rc;
     for (auto& d : ctx->devs) { CU(ctx, cudaSetDevice(d.dev)); CU(ctx, cudaStreamSynchronize(d.stream)); }
     if ((rc = check_watchdog(ctx)) != TRT_OK) return rc;
     if (stats) {
@@ -994,7 +1113,7 @@ static int trt_render_distributed_impl(trt_ctx* ctx, const trt_params* params, v
         d.last_launches = 0;
     }
     CU(ctx, cudaEventRecord(d.ev_c, d.stream));
-    if (rank == 0 && canva && albedo_tab && normal_tab) ensure_stage(d, sizeof(double) * 9 * npix);      // while the GPU traces
+    if (rank == 0 && !(host_is_pinned(canva) && host_is_pinned(albedo_tab) && host_is_pinned(normal_tab))) ensure_stage(d, sizeof(double) * 9 * npix);      // while the GPU traces
     if (n_ranks > 1 && (rc = trt_reduce_nccl(ctx, nccl_comm, (int64_t*)d.accum, 9 * npix, 0)) != TRT_OK) return rc;
     int launches = d.last_launches;
     if (rank == 0) {
@@ -1002,11 +1121,10 @@ static int trt_render_distributed_impl(trt_ctx* ctx, const trt_params* params, v
         trt_params rp = *params;
         if (rp.sample_total <= 0) rp.sample_total = spp;
         const long long* src = d.accum;
-        char* ob = (char*)d.out;
-        if ((rc = resolve_common(ctx, &rp, &src, 1, nullptr, (double*)(ob + canva8_bytes(npix)), (double*)(ob + canva8_bytes(npix)) + 3 * npix, (unsigned char*)ob)) != TRT_OK) return rc;
+        int mode = 0;
+        if ((rc = resolve_and_send(ctx, &rp, &src, 1, d, 0, npix, canva, albedo_tab, normal_tab, &mode)) != TRT_OK) return rc;
         launches++;
-        CU(ctx, cudaEventRecord(d.ev_d, d.stream));
-        if ((rc = copy_out(ctx, d, npix, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;
+        if ((rc = out_finish(ctx, d, npix, mode, canva, albedo_tab, normal_tab)) != TRT_OK) return rc;
     } else {
         CU(ctx, cudaEventRecord(d.ev_d, d.stream));
     }

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(256)
 resolve_kernel(ResolveArgs R)
 {
     const size_t npix = (size_t)R.W * (size_t)R.H;
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+    for (size_t p = R.p0 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < R.p1; p += (size_t)gridDim.x * blockDim.x) {
         long long s[9];
 #pragma unroll
         for (int c = 0; c < 9; c++) s[c] = 0;
@@ -292,6 +292,7 @@ resolve_kernel(ResolveArgs R)
 #pragma unroll
             for (int c = 0; c < 9; c++) s[c] += src[(size_t)c * npix + p];
         }
+        const size_t q = p - R.p0;
         const double rapport = 1.0 / (double)R.divisor;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
@@ -299,10 +300,10 @@ resolve_kernel(ResolveArgs R)
             float r = sqrtf((float)(rapport * sum));                 // sqrtf: FLOAT square root, like the reference
             double cl = (double)r;
             cl = cl < 0.0 ? 0.0 : (cl > 0.999 ? 0.999 : cl);         // NaN falls through both tests, as in clamp()
-            if (R.canva8) R.canva8[3 * p + c] = (unsigned char)(int)(256.0 * cl);
-            else R.canva[3 * p + c] = (double)(int)(256.0 * cl);
-            R.albedo[3 * p + c] = ((double)s[3 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
-            R.normal[3 * p + c] = ((double)s[6 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
+            if (R.canva8) R.canva8[3 * q + c] = (unsigned char)(int)(256.0 * cl);
+            else R.canva[3 * q + c] = (double)(int)(256.0 * cl);
+            R.albedo[3 * q + c] = ((double)s[3 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
+            R.normal[3 * q + c] = ((double)s[6 + c] * TRT_ACCUM_INV_SCALE) / (double)R.divisor;
         }
     }
 }
@@ -417,7 +418,8 @@ cudaError_t trt_launch_pathtrace(const RenderArgs& A, int n_sms, int blocks_per_
 
 cudaError_t trt_launch_resolve(const ResolveArgs& R, int n_sms, cudaStream_t stream)
 {
-    const size_t npix = (size_t)R.W * (size_t)R.H;
+    const size_t npix = R.p1 - R.p0;
+    if (npix == 0) return cudaSuccess;
     int grid = (int)((npix + 255) / 256);
     if (grid > n_sms * 8) grid = n_sms * 8;
     resolve_kernel<<<grid, 256, 0, stream>>>(R);

@@ -52,6 +52,7 @@ struct RenderArgs {
 
 struct ResolveArgs {
     int W, H, divisor, n_src;
+    size_t p0, p1;                      // pixels [p0, p1) of the frame; the output pointers are relative to p0 (a device resolves its own band)
     const long long* src[TRT_MAX_RESOLVE_SOURCES];
     double *canva, *albedo, *normal;    // [W*H][3]
     unsigned char* canva8;              // when set, canva is written here as 3 bytes per pixel instead (exact: the values are integers 0..255)

@@ -30,6 +30,14 @@ for flags, name in ((0, "spp split"), (trt.FLAG_TILE_SPLIT, "tile split")):
     st = b["stats"]
     print(f"C5 {n} GPUs in-process, {name}: {best:.2f} ms per frame (scene_set + trt_render), trace {st['ms_trace']:.2f} ms, reduce+resolve {st['ms_reduce_resolve']:.2f} ms, "
           f"d2h+host {st['ms_d2h']:.2f} ms, efficiency vs 1 GPU {t1 / (n * best):.3f}, bit-identical to 1 GPU: {sha(b) == h1}", flush=True)
+pinned = trt.host_arrays(npx, many.lib)
+for flags, name in ((0, "spp split, page-locked output arrays (trt_host_alloc)"),):
+    best = 1e9
+    for _ in range(4):
+        t0 = time.perf_counter(); many.scene_set(sc); b = many.render(S.params_for(sc, flags=flags), out=pinned); best = min(best, (time.perf_counter() - t0) * 1e3)
+    st = b["stats"]
+    print(f"C5 {n} GPUs in-process, {name}: {best:.2f} ms per frame, trace {st['ms_trace']:.2f} ms, reduce+resolve {st['ms_reduce_resolve']:.2f} ms, "
+          f"d2h {st['ms_d2h']:.2f} ms, efficiency vs 1 GPU {t1 / (n * best):.3f}, bit-identical to 1 GPU: {sha(b) == h1}", flush=True)
 many.close()
 exe = os.path.join(ROOT, "apps", "main_b200")
 subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "apps"), "main_b200"], stderr=subprocess.DEVNULL)
