@@ -391,7 +391,8 @@ def main():
         sc5, desc5 = workload("C5")
         rp5 = S.params_for(sc5)
         n5 = rp5.width * rp5.height
-        host5 = dict(canva=np.empty((n5, 3)), albedo=np.empty((n5, 3)), normal=np.empty((n5, 3))) if rank == 0 else None
+        # output arrays of rank 0: page-locked (trt_host_alloc), like apps/main_b200 allocates them; the N = 1 reference frame uses the same arrays
+        host5 = trt.host_arrays(n5, r.lib) if rank == 0 else None
 
         def step_c5():
             r.scene_set(sc5)
@@ -411,7 +412,7 @@ def main():
             rays5, trace5 = float(t5[1]), float(t5[2])
         strong = {"workload": desc5, "n_gpus": world, "steps": c5_steps, "ms_per_frame": t5_ms / c5_steps, "trace_ms_max_rank": trace5,
                   "mrays_s": rays5 / (t5_ms * 1e-3) / 1e6, "msamples_s": n5 * rp5.spp * c5_steps / (t5_ms * 1e-3) / 1e6,
-                  "what": "trt_scene_set + trt_render_distributed (trace of spp/N, ncclReduce int64, resolve, D2H on rank 0), host buffers, max over ranks"}
+                  "what": "trt_scene_set + trt_render_distributed (trace of spp/N, ncclReduce int64, resolve, D2H on rank 0), page-locked host output arrays (trt_host_alloc), max over ranks"}
         if world > 1:
             if rank == 0:
                 h_n = sha(host5)
