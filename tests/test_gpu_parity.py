@@ -351,6 +351,11 @@ def test_edge_cases_and_errors(oracle):
         fresh.render(S.RenderParams(width=1, height=1, spp=1, bounces=1, cam=sc.camera()))
     with pytest.raises(TrtError):
         fresh.render(S.params_for(sc, width=8, spp=0))
+    # useAO with an AO_intensity that ThreadData's int truncation turns into 0 (main.c:42): 1/AO is a division by zero in main.c:115
+    bad = S.params_for(sc, width=8, spp=1)
+    bad.ao_intensity = 0.4
+    with pytest.raises(TrtError, match="AO_intensity"):
+        fresh.render(bad)
     # smallest legal image, one sample, zero bounces: black radiance, AOVs untouched (loop never runs)
     r = fresh.render(S.RenderParams(width=2, height=2, spp=1, bounces=0, cam=sc.camera()))
     assert not r["canva"].any() and not r["albedo"].any()
