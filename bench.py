@@ -61,6 +61,15 @@ def workload(name: str):
     return sc, desc
 
 
+def job_config(desc, sc, spp, world, seed) -> dict:
+    """The `config` object of the JSON line: the SAME dict on the GPU arm and on the reference arm (the reference arm's bounded sample is
+    described in its `cpu_baseline.sample`, not here)."""
+    return {"workload": desc, "width": sc.width, "height": sc.height, "spp_per_gpu": spp, "spp_total": spp * world,
+            "nbRebondMax": sc.bounces, "useAO": bool(sc.use_ao), "seed": seed,
+            "l2": "512 MB buffer written between timed steps (L2 flush)",
+            "parallelism": f"spp-split x{world}, int64 ncclReduce issued by libtipe_rt (trt_reduce_nccl)" if world > 1 else "single GPU"}
+
+
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
     """SM clock + throttle reasons WHILE the timed region runs (B200_PROFILING.md recipe).  NVML is polled in-process
@@ -174,12 +183,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     value, sec, info, n = cpu_reference_run(args.config, args.steps, args.warmup, budget_s=60.0)
-    _, desc = workload(args.config)
+    sc, desc = workload(args.config)
+    from tipe_raytracer_b200 import scene as S
     info["value"] = value
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1),
         "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic", "config": {"workload": desc, "sample": info["sample"]},
+        "data": "synthetic", "config": job_config(desc, sc, args.spp or sc.spp, args.gpus, S.params_for(sc).seed),
         "cpu_baseline": {**info, "unit": UNIT},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -475,10 +485,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp * world,
-                       "nbRebondMax": sc.bounces, "useAO": bool(sc.use_ao), "seed": rp.seed,
-                       "l2": "512 MB buffer written between timed steps (L2 flush)",
-                       "parallelism": f"spp-split x{world}, int64 ncclReduce issued by libtipe_rt (trt_reduce_nccl)" if world > 1 else "single GPU"},
+            "config": job_config(desc, sc, spp, world, rp.seed),
             "rays_per_step": rays_total / steps, "rays_per_path": rays_local / steps / (npix * spp),
             "nominal_mrays_s": npix * spp * world * sc.bounces / (ms_per_step * 1e-3) / 1e6,
             "msamples_s": npix * spp * world / (ms_per_step * 1e-3) / 1e6,
