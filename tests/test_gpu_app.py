@@ -40,7 +40,8 @@ def test_mini_scene_matches_oracle_same_stream(rt, oracle):
     g = rt.render(rp)
     o = oracle.render(sc, rp, rng=RNG_PHILOX)
     d = np.abs(g["canva"] - o["canva"])
-    assert (d.max(axis=1) <= 1).mean() > 0.95 and d.mean() < 0.6, ((d.max(axis=1) <= 1).mean(), d.mean())
+    print(f"mini scene vs oracle: within 1 LSB {(d.max(axis=1) <= 1).mean():.4f}, mean |diff| {d.mean():.4f}")
+    assert (d.max(axis=1) <= 1).mean() > 0.995 and d.mean() < 0.05, ((d.max(axis=1) <= 1).mean(), d.mean())     # observed 1.0 / 0.0
     assert abs(g["stats"]["rays"] / o["stats"]["rays"] - 1) < 5e-3
     prim_g, prim_o = rt.primary(rp), oracle.primary(sc, rp)
     assert np.array_equal(prim_g["id"], prim_o["id"]) and np.array_equal(prim_g["t"], prim_o["t"])

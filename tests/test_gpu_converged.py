@@ -114,5 +114,7 @@ def test_many_spheres_need_more_than_48k_shared_memory(rt, oracle):
     rp = S.params_for(sc)
     g = rt.render(rp)
     o = oracle.render(sc, rp, rng=RNG_PHILOX)
-    assert (np.abs(g["canva"] - o["canva"]).max(axis=1) <= 1).mean() >= 0.97
+    w1 = (np.abs(g["canva"] - o["canva"]).max(axis=1) <= 1).mean()
+    print(f"600 spheres: within 1 LSB {w1:.4f}, rays {g['stats']['rays'] / o['stats']['rays'] - 1:+.2e}")
+    assert w1 >= 0.98                 # observed 0.9909 (599 small glossy spheres: many silhouettes per pixel)
     assert abs(g["stats"]["rays"] / o["stats"]["rays"] - 1) < 5e-3

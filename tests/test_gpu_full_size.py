@@ -51,6 +51,8 @@ def test_full_size_sample_ranges_add_up_exactly(rt, cfg):
     n = rp.width * rp.height
     lin_gpu = full.view(9, n)[:3].double().mean(dim=1).cpu().numpy() / D.ACCUM_SCALE / rp.spp
     lin_cpu = o["sums"][:, :3].mean(0) / small.spp
+    print(f"{cfg} full size vs oracle at 96 px x 8 spp: rays/path {st['rays'] / st['paths']:.4f} vs {o['stats']['rays'] / o['stats']['paths']:.4f}, "
+          f"linear radiance mean ratio {lin_gpu / lin_cpu}")          # the bar is the noise of the 8-spp oracle image, not the GPU's
     assert np.abs(lin_gpu / lin_cpu - 1).max() < 0.05, (lin_gpu, lin_cpu)
 
 
@@ -83,6 +85,8 @@ def test_full_size_c5_readme_benchmark_statistics(rt, oracle):
     n = rp.width * rp.height
     lin_gpu = acc.view(9, n)[:3].double().mean(dim=1).cpu().numpy() / D.ACCUM_SCALE / rp.spp
     lin_cpu = o["sums"][:, :3].mean(0) / small.spp
+    print(f"C5 full size vs oracle at 150 px x 24 spp: rays/path {st['rays'] / st['paths']:.4f} vs {o['stats']['rays'] / o['stats']['paths']:.4f}, "
+          f"linear radiance mean ratio {lin_gpu / lin_cpu}, albedo mean diff {np.abs(res['albedo'].mean(0) - o['albedo'].mean(0)).max():.2e}")
     assert np.abs(lin_gpu / lin_cpu - 1).max() < 0.03, (lin_gpu, lin_cpu)        # unbiased linear means
     assert np.abs(res["albedo"].mean(0) - o["albedo"].mean(0)).max() < 0.01
     assert res["canva"].max() <= 255 and res["canva"].min() >= 0
@@ -104,7 +108,9 @@ def test_c4big_one_million_triangles(rt, oracle):
     b = rt.render(S.params_for(sc, width=32, spp=2, flags=FLAG_BRUTE_FORCE))
     assert np.array_equal(a["canva"], b["canva"]) and np.array_equal(a["albedo"], b["albedo"]) and a["stats"]["rays"] == b["stats"]["rays"]
     o = oracle.render(sc, tiny, rng=RNG_PHILOX)
-    assert (np.abs(a["canva"] - o["canva"]).max(axis=1) <= 1).mean() >= 0.95
+    w1 = (np.abs(a["canva"] - o["canva"]).max(axis=1) <= 1).mean()
+    print(f"C4big 32x18x2 vs oracle: within 1 LSB {w1:.4f}, rays {a['stats']['rays'] / o['stats']['rays'] - 1:+.2e}")
+    assert w1 >= 0.99                 # observed 1.0
     assert abs(a["stats"]["rays"] / o["stats"]["rays"] - 1) < 1e-2
     mid = S.params_for(sc, width=480, spp=1)
     exact, fast = rt.primary(mid), rt.primary_fp32(mid)

@@ -120,41 +120,44 @@ def _compare_same_stream(rt, oracle, sc, rp, min_within1, max_mean_abs):
     o = oracle.render(sc, rp, rng=RNG_PHILOX)
     d = np.abs(g["canva"] - o["canva"])
     within1 = (d.max(axis=1) <= 1).mean()
+    rays_gpu, rays_cpu = g["stats"]["rays"], o["stats"]["rays"]
+    alb, nrm = np.abs(g["albedo"] - o["albedo"]).mean(), np.abs(g["normal"] - o["normal"]).mean()
+    print(f"same-stream {sc.name} {rp.width}x{rp.height}x{rp.spp}: within 1 LSB {within1:.4f} (bar {min_within1}), mean |diff| {d.mean():.4f} "
+          f"(bar {max_mean_abs}), max |diff| {d.max():.0f}, rays {rays_gpu / rays_cpu - 1:+.2e}, albedo mean |diff| {alb:.2e}, normal {nrm:.2e}")
     assert within1 >= min_within1, (within1, d.mean())
     assert d.mean() <= max_mean_abs, d.mean()
-    rays_gpu, rays_cpu = g["stats"]["rays"], o["stats"]["rays"]
-    assert abs(rays_gpu / rays_cpu - 1) < 5e-3, (rays_gpu, rays_cpu)
-    assert np.abs(g["albedo"] - o["albedo"]).mean() < 2e-3 and np.abs(g["normal"] - o["normal"]).mean() < 2e-3
+    assert abs(rays_gpu / rays_cpu - 1) < 5e-4, (rays_gpu, rays_cpu)       # observed <= 5.4e-5
+    assert alb < 1e-3 and nrm < 3e-4                                        # observed <= 2.2e-4 (quarter-res textures) / 5.3e-5
     return g, o
 
 
 def test_render_c1_same_stream(rt, oracle):
     sc = S.cornell_spheres()
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=160, spp=16), 0.97, 0.25)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=160, spp=16), 0.995, 0.05)        # observed 0.9996 / 0.008
 
 
 def test_render_c1_no_ao_with_aperture(rt, oracle):
     sc = S.cornell_spheres()
     sc.use_ao = False
     sc.aperture = (1.0, 2.0)            # >= 1 so main.c's int truncation keeps them
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=120, spp=12), 0.97, 0.25)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=120, spp=12), 0.995, 0.08)        # observed 0.9994 / 0.022
 
 
 def test_render_c3_refraction_stack_same_stream(rt, oracle):
     sc = S.nested_dielectrics()
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=120, spp=12), 0.95, 0.4)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=120, spp=12), 0.99, 0.25)         # observed 0.9983 / 0.077
 
 
 def test_render_c2_mesh_same_stream(rt, oracle):
     sc = S.nature_mesh()
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.995, 0.05)            # observed 0.9996 .. 1.0 / <= 0.006
     assert rt.bvh_info()["n_twins"] > 1000          # double-faced mesh: twins found
 
 
 def test_render_c2b_water_mesh_same_stream(rt, oracle):
     """The second textured mesh SURVEY §8d names (model3D/water): single-faced, so no twins, 17 materials with light / glass / water ordinals."""
     sc = S.water_mesh()
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.995, 0.05)            # observed 0.9996 .. 1.0 / <= 0.006
     prim_g, prim_o = rt.primary(S.params_for(sc, width=200, spp=1)), oracle.primary(sc, S.params_for(sc, width=200, spp=1))
     assert np.array_equal(prim_g["id"], prim_o["id"]) and np.array_equal(prim_g["t"], prim_o["t"]) and (prim_g["id"] >= 1).mean() > 0.2
     a = rt.render(S.params_for(sc, width=96, spp=4, flags=FLAG_BRUTE_FORCE))
@@ -164,7 +167,7 @@ def test_render_c2b_water_mesh_same_stream(rt, oracle):
 
 def test_render_c4_tree_same_stream(rt, oracle):
     sc = S.tree_mesh()
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.995, 0.05)            # observed 0.9996 .. 1.0 / <= 0.006
 
 
 def test_render_c4_sky_texture_same_stream(rt, oracle):
@@ -172,13 +175,15 @@ def test_render_c4_sky_texture_same_stream(rt, oracle):
     sphere of radius 1e5 against the FP64 oracle, same Philox stream; and switching it off restores the plain image."""
     sc = S.tree_mesh_sky()
     rp = S.params_for(sc, width=160, spp=8)
-    g, o = _compare_same_stream(rt, oracle, sc, rp, 0.95, 0.6)
+    g, o = _compare_same_stream(rt, oracle, sc, rp, 0.995, 0.05)      # observed 0.9999 / 0.0004
     assert len(np.unique(g["canva"], axis=0)) > 200          # the gradient + sun are visible, not one flat colour
     plain = S.tree_mesh()
     rt.scene_set(plain)                                       # scene without sky => trt_sky_set(NULL)
     g2 = rt.render(rp)
     o2 = oracle.render(plain, rp, rng=RNG_PHILOX)
-    assert (np.abs(g2["canva"] - o2["canva"]).max(axis=1) <= 1).mean() >= 0.95
+    w1 = (np.abs(g2["canva"] - o2["canva"]).max(axis=1) <= 1).mean()
+    print(f"tree mesh after sky off: within 1 LSB {w1:.4f}")
+    assert w1 >= 0.995                # observed 0.9999
     assert not np.array_equal(g["canva"], g2["canva"])
 
 
@@ -186,7 +191,7 @@ def test_render_mesh_with_ambient_occlusion_same_stream(rt, oracle):
     """AO rays against a BVH (any-hit traversal, alpha ignored: main.c:104-106) — what main.c does when useAO stays true with a mesh."""
     sc = S.nature_mesh()
     sc.use_ao = True
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.95, 0.6)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=96, spp=4), 0.995, 0.05)            # observed 0.9996 .. 1.0 / <= 0.006
     a = rt.render(S.params_for(sc, width=96, spp=4, flags=FLAG_BRUTE_FORCE))          # linear scan = BVH, AO included
     b = rt.render(S.params_for(sc, width=96, spp=4))
     assert np.array_equal(a["canva"], b["canva"]) and a["stats"]["rays"] == b["stats"]["rays"]
@@ -204,7 +209,7 @@ def test_render_spheres_and_mesh_mixed_with_ao_same_stream(rt, oracle):
     sc.use_ao = True
     sc.cam_origin, sc.cam_target, sc.vfov, sc.ratio = box.cam_origin, box.cam_target, box.vfov, box.ratio
     rp = S.params_for(sc, width=128, spp=8, bounces=5)
-    g, o = _compare_same_stream(rt, oracle, sc, rp, 0.93, 0.8)
+    g, o = _compare_same_stream(rt, oracle, sc, rp, 0.995, 0.05)      # observed 0.9993 / 0.007
     prim_g, prim_o = rt.primary(rp), oracle.primary(sc, rp)
     assert np.array_equal(prim_g["id"], prim_o["id"])
     assert (prim_g["id"] >= 10).mean() > 0.03 and (prim_g["id"] < 10).mean() > 0.5   # both kinds of primitive are seen
@@ -214,7 +219,7 @@ def test_render_c3b_pyramide_eau_same_stream(rt, oracle):
     """The scene main.c ships configured for: light / glass / water overrides, 20 bounces, coordinates up to 1800
     (FP32 ulp there is 1e-4, a thousand times the reference's 1e-7 triangle threshold)."""
     sc = S.pyramide_eau()
-    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=128, spp=8), 0.90, 1.5)
+    _compare_same_stream(rt, oracle, sc, S.params_for(sc, width=128, spp=8), 0.98, 0.3)            # observed 0.9915 / 0.091
 
 
 def test_bvh_equals_linear_scan(rt):
@@ -282,7 +287,9 @@ def test_leaf_runs_edge_cases(rt, oracle, case):
     b = rt.render(S.params_for(sc, flags=FLAG_BRUTE_FORCE))
     assert np.array_equal(a["canva"], b["canva"]) and np.array_equal(a["albedo"], b["albedo"]) and a["stats"]["rays"] == b["stats"]["rays"]
     o = oracle.render(sc, rp, rng=RNG_PHILOX)
-    assert (np.abs(a["canva"] - o["canva"]).max(axis=1) <= 1).mean() >= 0.97
+    w1 = (np.abs(a["canva"] - o["canva"]).max(axis=1) <= 1).mean()
+    print(f"equal-box runs scene: within 1 LSB {w1:.4f}")
+    assert w1 >= 0.995                # observed 1.0 on all four layouts
     assert abs(a["stats"]["rays"] / o["stats"]["rays"] - 1) < 5e-3
 
 
@@ -363,7 +370,9 @@ def test_edge_cases_and_errors(oracle):
     rp = S.params_for(sc, width=61, spp=37)
     g = fresh.render(rp)
     o = oracle.render(sc, rp, rng=RNG_PHILOX)
-    assert (np.abs(g["canva"] - o["canva"]).max(axis=1) <= 1).mean() > 0.97
+    w1 = (np.abs(g["canva"] - o["canva"]).max(axis=1) <= 1).mean()
+    print(f"ragged 61-wide x 37 spp: within 1 LSB {w1:.4f}")
+    assert w1 >= 0.995                # observed 0.9993
     # empty scene: every ray misses
     empty = S.Scene(name="empty", spheres=np.zeros(0, S.SPHERE), triangles=np.zeros(0, S.TRIANGLE), mat_list=np.zeros(0, S.MATERIAL))
     fresh.scene_set(empty)
