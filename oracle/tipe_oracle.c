@@ -50,7 +50,7 @@ static inline void to_ptr(v3 a, double* p) { p[0] = a.x[0]; p[1] = a.x[1]; p[2] 
  *         counter = (pixel_index, global sample index, slot, 0); uniform = (x >> 8) * 2^-24.
  *   slot 0        : x0 pixel jitter u, x1 pixel jitter v, x2 aperture dx, x3 aperture dy (main.c:265-269)
  *   slot 1 + 2*i  : bounce i — x0,x1 diffuse direction (main.c:163); x2,x3 AO direction (main.c:100)
- *   slot 2 + 2*i  : bounce i — x0 refraction coin (main.c:185)
+ *   slot 2 + 2*i  : bounce i — x0 refraction coin (main.c:185) when useAO; without AO the coin is x2 of slot 1 + 2*i (unused there)
  * ---------------------------------------------------------------------------------------- */
 API void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
@@ -408,7 +408,7 @@ static void trace_path(const oracle_scene* sc, v3 o, v3 d, int nbRebondMax, doub
                 n1 = top[1]; n2 = top[0];
             }
             v3 refracted = refract_dir(d, n, n1, n2);
-            double coin = rng_range(g, slot_coin(i), 0, 0, 1);
+            double coin = useAO ? rng_range(g, slot_coin(i), 0, 0, 1) : rng_range(g, slot_bounce(i), 2, 0, 1);
             if (coin > m.alpha) { d = refracted; continue; }
             else d = mixed;
         }
