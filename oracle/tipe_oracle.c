@@ -50,7 +50,8 @@ static inline void to_ptr(v3 a, double* p) { p[0] = a.x[0]; p[1] = a.x[1]; p[2] 
  *         counter = (pixel_index, global sample index, slot, 0); uniform = (x >> 8) * 2^-24.
  *   slot 0        : x0 pixel jitter u, x1 pixel jitter v, x2 aperture dx, x3 aperture dy (main.c:265-269)
  *   slot 1 + 2*i  : bounce i — x0,x1 diffuse direction (main.c:163); x2,x3 AO direction (main.c:100)
- *   slot 2 + 2*i  : bounce i — x0 refraction coin (main.c:185) when useAO; without AO the coin is x2 of slot 1 + 2*i (unused there)
+ *                   refraction coin (main.c:185) = the low bytes of x0, x1, x2 of the same block (24 bits the uniforms above never read)
+ *   slot 2 + 2*i  : unused (held the coin until round 2)
  * ---------------------------------------------------------------------------------------- */
 API void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
 {
@@ -75,7 +76,6 @@ typedef struct {
 
 enum { SLOT_CAMERA = 0 };
 static inline uint32_t slot_bounce(int i) { return 1u + 2u * (uint32_t)i; }
-static inline uint32_t slot_coin(int i) { return 2u + 2u * (uint32_t)i; }
 
 static double rng_u01(rng_t* g, uint32_t slot, int lane)
 {
@@ -86,6 +86,16 @@ static double rng_u01(rng_t* g, uint32_t slot, int lane)
         g->cached_slot = slot; g->cache_valid = 1;
     }
     return (double)(g->cache[lane] >> 8) * (1.0 / 16777216.0);
+}
+
+/* the refraction coin: one randomDouble(0,1) in libc mode; in Philox mode 24 bits taken from the low bytes of words 0-2 of the
+ * bounce's block (rng_u01 uses the top 24 bits of a word, so these are independent of every direction drawn from the block) */
+static double rng_coin(rng_t* g, uint32_t slot)
+{
+    if (g->mode == TRT_ORACLE_RNG_LIBC) return rand() / (RAND_MAX + 1.0);
+    (void)rng_u01(g, slot, 0);                                   /* fills the cache for this slot */
+    uint32_t bits = (g->cache[0] & 0xffu) | ((g->cache[1] & 0xffu) << 8) | ((g->cache[2] & 0xffu) << 16);
+    return (double)bits * (1.0 / 16777216.0);
 }
 
 /* randomDouble(min,max) = min + (max-min)*u  (rtutility.h:229-231) */
@@ -408,7 +418,7 @@ static void trace_path(const oracle_scene* sc, v3 o, v3 d, int nbRebondMax, doub
                 n1 = top[1]; n2 = top[0];
             }
             v3 refracted = refract_dir(d, n, n1, n2);
-            double coin = useAO ? rng_range(g, slot_coin(i), 0, 0, 1) : rng_range(g, slot_bounce(i), 2, 0, 1);
+            double coin = rng_coin(g, slot_bounce(i));
             if (coin > m.alpha) { d = refracted; continue; }
             else d = mixed;
         }
